@@ -1,0 +1,518 @@
+// mmm_api.cu — the extern "C" surface declared in include/multimm_b200.h, plus handle
+// bookkeeping.  Host code only; every kernel lives in the sibling .cu files.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "mmm_internal.cuh"
+
+int mmm_launch_dots_decide(mmm_system* h);  // mmm_lbfgs.cu
+
+static thread_local std::string g_create_error;
+
+int mmm_fail(mmm_system* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define REQUIRE(h, cond, msg) \
+  do { if (!(cond)) return mmm_fail((h), MMM_ERR_ARG, (msg)); } while (0)
+
+template <typename T>
+static int dev_alloc(mmm_system* h, T** p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) return MMM_OK;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess)
+    return mmm_fail(h, MMM_ERR_NOMEM, std::string("CUDA error: ") + cudaGetErrorString(e) + " (cudaMalloc)");
+  return MMM_OK;
+}
+
+static void derive_pair_params(mmm_system* h) {
+  PairParams& p = h->pp;
+  p.ev_pref = p.ev_form == MMM_EV_POWERLAW ? p.ev_eps * powf(p.ev_sigma, p.ev_power) : 0.0f;
+  const float rc = p.scb_form >= 0 ? p.scb_rc : p.cob_rc;
+  if (rc > 0.0f) {
+    p.g_c = -1.4426950408889634f / (2.0f * rc * rc);
+    p.g_inv_rc2 = 1.0f / (rc * rc);
+    p.rg2 = 2.0f * rc * rc * 40.0f * 0.6931471805599453f;  // exp(-rg^2 / 2rc^2) = 2^-40
+  } else {
+    p.g_c = 0.0f; p.g_inv_rc2 = 0.0f; p.rg2 = 0.0f;
+  }
+  p.cutoff2 = (float)h->cutoff * (float)h->cutoff;
+}
+
+extern "C" {
+
+int mmm_abi_version(void) { return MMM_ABI_VERSION; }
+
+const char* mmm_last_error(mmm_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mmm_create(int device, int64_t n_beads, mmm_handle* out) {
+  if (!out) return mmm_fail(nullptr, MMM_ERR_ARG, "mmm_create: out is NULL");
+  *out = nullptr;
+  if (n_beads < 2 || n_beads > (int64_t)1 << 27)
+    return mmm_fail(nullptr, MMM_ERR_ARG, "mmm_create: n_beads must be in [2, 2^27]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return mmm_fail(nullptr, MMM_ERR_CUDA,
+                    std::string("CUDA error: no usable device (") + cudaGetErrorString(e) +
+                        "); this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return mmm_fail(nullptr, MMM_ERR_ARG, "mmm_create: device index out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return mmm_fail(nullptr, MMM_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+  if (prop.major != 10)
+    return mmm_fail(nullptr, MMM_ERR_CUDA,
+                    "CUDA error: device is not sm_100 (B200); the kernels are built for sm_100a only");
+  mmm_system* h = new (std::nothrow) mmm_system();
+  if (!h) return mmm_fail(nullptr, MMM_ERR_NOMEM, "out of host memory");
+  h->device = device;
+  h->n = n_beads;
+  h->npad = (n_beads + MMM_IBLOCK - 1) / MMM_IBLOCK * MMM_IBLOCK;
+  h->ntiles = h->npad / MMM_TILE;
+  h->sm_count = prop.multiProcessorCount;
+  h->pp.ev_form = h->pp.cob_form = h->pp.scb_form = h->pp.chb_form = MMM_FORM_OFF;
+  h->ep.sc_form = h->ep.lam_form = h->ep.cf_form = MMM_FORM_OFF;
+  h->n_red_blocks = (int)((n_beads + MMM_ASM_BLOCK - 1) / MMM_ASM_BLOCK);
+  h->n_dot_blocks = std::min(h->n_red_blocks, 2 * h->sm_count);
+  int rc = MMM_OK;
+  auto fail = [&](int code) { g_create_error = h->err; mmm_destroy(h); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(mmm_fail(h, MMM_ERR_CUDA, "CUDA error: cudaSetDevice"));
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(mmm_fail(h, MMM_ERR_CUDA, "CUDA error: cudaStreamCreate"));
+  cudaEventCreate(&h->ev_a);
+  cudaEventCreate(&h->ev_b);
+  const size_t n3 = 3 * (size_t)n_beads;
+  if ((rc = dev_alloc(h, &h->d_type, (size_t)h->npad))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_cstr, (size_t)n_beads))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_s, (size_t)n_beads))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_x, n3))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_center, 3))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_pos4, (size_t)h->npad))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_tiles, (size_t)h->ntiles))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_g, n3))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_counter, 4))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_epart, (size_t)h->n_red_blocks * 6))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_dpart, (size_t)h->n_red_blocks * MMM_NDOT))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_eterms, MMM_NUM_TERMS))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_lb, 1))) return fail(rc);
+  if (cudaMallocHost((void**)&h->h_done, 64) != cudaSuccess)
+    return fail(mmm_fail(h, MMM_ERR_NOMEM, "CUDA error: cudaMallocHost"));
+  cudaMemsetAsync(h->d_cstr, 0, sizeof(double) * n_beads, h->stream);
+  cudaMemsetAsync(h->d_s, 0, n_beads, h->stream);
+  cudaMemsetAsync(h->d_lb, 0, sizeof(LbfgsState), h->stream);
+  std::vector<int> ty((size_t)h->npad, mmm_pack_type(0, MMM_PAD_CHROM));
+  for (int64_t i = 0; i < n_beads; ++i) ty[i] = mmm_pack_type(0, 0);
+  cudaMemcpyAsync(h->d_type, ty.data(), sizeof(int) * ty.size(), cudaMemcpyHostToDevice, h->stream);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess)
+    return fail(mmm_fail(h, MMM_ERR_CUDA, "CUDA error: initialisation copies failed"));
+  h->types_dirty = false;
+  *out = h;
+  return MMM_OK;
+}
+
+int mmm_destroy(mmm_handle h) {
+  if (!h) return MMM_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  void* ptrs[] = {h->d_type, h->d_cstr, h->d_s, h->d_bl_ptr, h->d_bl_partner, h->d_bl_flags, h->d_bl_r0, h->d_bl_k,
+                  h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_tiles, h->d_g,
+                  h->d_fpair, h->d_epair, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
+                  h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
+                  h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_done) cudaFreeHost(h->h_done);
+  if (h->ev_a) cudaEventDestroy(h->ev_a);
+  if (h->ev_b) cudaEventDestroy(h->ev_b);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MMM_OK;
+}
+
+// ---- topology --------------------------------------------------------------------------
+static int check_pairs(mmm_system* h, const int32_t* i, const int32_t* j, int64_t cnt, const char* what) {
+  for (int64_t q = 0; q < cnt; ++q)
+    if (i[q] < 0 || j[q] < 0 || i[q] >= h->n || j[q] >= h->n || i[q] == j[q])
+      return mmm_fail(h, MMM_ERR_ARG, std::string(what) + ": bead index out of range or degenerate");
+  return MMM_OK;
+}
+
+int mmm_set_bonds(mmm_handle h, const int32_t* i, const int32_t* j, const double* r0, const double* k,
+                  int64_t n_bonds) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, n_bonds >= 0 && (n_bonds == 0 || (i && j && r0 && k)), "mmm_set_bonds: NULL array");
+  int rc = check_pairs(h, i, j, n_bonds, "mmm_set_bonds");
+  if (rc) return rc;
+  h->h_bond_i.assign(i, i + n_bonds); h->h_bond_j.assign(j, j + n_bonds);
+  h->h_bond_r0.assign(r0, r0 + n_bonds); h->h_bond_k.assign(k, k + n_bonds);
+  h->n_bonds = n_bonds;
+  h->topo_dirty = true;
+  return MMM_OK;
+}
+
+int mmm_set_loops(mmm_handle h, const int32_t* i, const int32_t* j, const double* r0, const double* k,
+                  int64_t n_loops, int form) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, form >= MMM_LOOP_HARMONIC && form <= MMM_LOOP_GAUSSIAN_TETHER, "Unknown loop force type");
+  REQUIRE(h, n_loops >= 0 && (n_loops == 0 || (i && j && r0 && k)), "mmm_set_loops: NULL array");
+  int rc = check_pairs(h, i, j, n_loops, "mmm_set_loops");
+  if (rc) return rc;
+  h->h_loop_i.assign(i, i + n_loops); h->h_loop_j.assign(j, j + n_loops);
+  h->h_loop_r0.assign(r0, r0 + n_loops); h->h_loop_k.assign(k, k + n_loops);
+  h->n_loops = n_loops;
+  h->loop_form = form;
+  h->topo_dirty = true;
+  return MMM_OK;
+}
+
+int mmm_set_angles(mmm_handle h, const int32_t* i, const int32_t* j, const int32_t* k, const double* theta0,
+                   const double* k_theta, int64_t n_angles) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, n_angles >= 0 && (n_angles == 0 || (i && j && k && theta0 && k_theta)), "mmm_set_angles: NULL array");
+  for (int64_t q = 0; q < n_angles; ++q)
+    if (i[q] < 0 || j[q] < 0 || k[q] < 0 || i[q] >= h->n || j[q] >= h->n || k[q] >= h->n)
+      return mmm_fail(h, MMM_ERR_ARG, "mmm_set_angles: bead index out of range");
+  cudaSetDevice(h->device);
+  return mmm_upload_angles(h, i, j, k, theta0, k_theta, n_angles);
+}
+
+int mmm_set_bead_params(mmm_handle h, const int8_t* s, const int32_t* chrom, const double* chrom_strength) {
+  if (!h) return MMM_ERR_ARG;
+  cudaSetDevice(h->device);
+  std::vector<int> ty((size_t)h->npad, mmm_pack_type(0, MMM_PAD_CHROM));
+  std::vector<signed char> sv((size_t)h->n, 0);
+  for (int64_t i = 0; i < h->n; ++i) {
+    const int si = s ? (int)s[i] : 0;
+    const int ci = chrom ? chrom[i] : 0;
+    if (si < -2 || si > 2) return mmm_fail(h, MMM_ERR_ARG, "mmm_set_bead_params: compartment label outside [-2, 2]");
+    if (ci < 0 || ci >= MMM_PAD_CHROM) return mmm_fail(h, MMM_ERR_ARG, "mmm_set_bead_params: chromosome id outside [0, 65534]");
+    ty[i] = mmm_pack_type(si, ci);
+    sv[i] = (signed char)si;
+  }
+  MMM_CUDA(h, cudaMemcpyAsync(h->d_type, ty.data(), sizeof(int) * ty.size(), cudaMemcpyHostToDevice, h->stream));
+  MMM_CUDA(h, cudaMemcpyAsync(h->d_s, sv.data(), sv.size(), cudaMemcpyHostToDevice, h->stream));
+  if (chrom_strength)
+    MMM_CUDA(h, cudaMemcpyAsync(h->d_cstr, chrom_strength, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+  else
+    MMM_CUDA(h, cudaMemsetAsync(h->d_cstr, 0, sizeof(double) * h->n, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMM_OK;
+}
+
+int mmm_set_pair_term(mmm_handle h, int term, int form, const double* g, int ng) {
+  if (!h) return MMM_ERR_ARG;
+  PairParams& p = h->pp;
+  REQUIRE(h, form == MMM_FORM_OFF || g, "mmm_set_pair_term: globals is NULL");
+  switch (term) {
+    case MMM_TERM_EV:
+      REQUIRE(h, form >= -1 && form <= MMM_EV_GAUSSIAN_CORE, "Unknown EV_FORCE_TYPE");
+      p.ev_form = form;
+      if (form >= 0) {
+        REQUIRE(h, ng >= 4, "EV needs {epsilon, r_small, sigma, power}");
+        p.ev_eps = (float)g[0]; p.ev_rs = (float)g[1]; p.ev_sigma = (float)g[2]; p.ev_power = (float)g[3];
+      }
+      break;
+    case MMM_TERM_COB:
+      REQUIRE(h, form >= -1 && form <= MMM_BLOCK_THETA, "Unknown COB_FORCE_TYPE");
+      p.cob_form = form;
+      if (form >= 0) {
+        REQUIRE(h, ng >= 3, "COB needs {rc, Ea, Eb}");
+        p.cob_rc = (float)g[0]; p.cob_ea = (float)g[1]; p.cob_eb = (float)g[2];
+      }
+      break;
+    case MMM_TERM_SCB:
+      REQUIRE(h, form >= -1 && form <= MMM_BLOCK_THETA, "Unknown SCB_FORCE_TYPE");
+      p.scb_form = form;
+      if (form >= 0) {
+        REQUIRE(h, ng >= 5, "SCB needs {rsc, Ea1, Ea2, Eb1, Eb2}");
+        p.scb_rc = (float)g[0];
+        for (int q = 0; q < 4; ++q) p.scb_e[q] = (float)g[1 + q];
+      }
+      break;
+    case MMM_TERM_CHB:
+      REQUIRE(h, form >= -1 && form <= MMM_CHB_SATURATING, "Unknown CHB_FORCE_TYPE");
+      p.chb_form = form;
+      if (form >= 0) {
+        REQUIRE(h, ng >= 2, "CHB needs {k_C, dE}");
+        p.chb_kc = (float)g[0]; p.chb_de = (float)g[1];
+      }
+      break;
+    default:
+      return mmm_fail(h, MMM_ERR_ARG, "mmm_set_pair_term: term is not a pair term");
+  }
+  derive_pair_params(h);
+  return MMM_OK;
+}
+
+int mmm_set_external_term(mmm_handle h, int term, int form, const double* g, int ng) {
+  if (!h) return MMM_ERR_ARG;
+  ExternalParams& p = h->ep;
+  REQUIRE(h, form == MMM_FORM_OFF || g, "mmm_set_external_term: globals is NULL");
+  switch (term) {
+    case MMM_TERM_SC:
+      REQUIRE(h, form >= -1 && form <= MMM_SC_DOUBLE_WALL, "Unknown spherical container form");
+      p.sc_form = form;
+      if (form >= 0) { REQUIRE(h, ng >= 6, "SC needs {C, R1, R2, x0, y0, z0}"); memcpy(p.sc, g, 6 * sizeof(double)); }
+      break;
+    case MMM_TERM_LAM:
+      REQUIRE(h, form >= -1 && form <= MMM_LAM_LOGISTIC_SHELL, "Unknown BLAMINA_FORCE_TYPE");
+      p.lam_form = form;
+      if (form >= 0) { REQUIRE(h, ng >= 6, "LAM needs {B, R1, R2, x0, y0, z0}"); memcpy(p.lam, g, 6 * sizeof(double)); }
+      break;
+    case MMM_TERM_CF:
+      REQUIRE(h, form >= -1 && form <= MMM_CF_LOGISTIC, "Unknown CENTRAL_FORCE_TYPE");
+      p.cf_form = form;
+      if (form >= 0) { REQUIRE(h, ng >= 5, "CF needs {G, R1, x0, y0, z0}"); memcpy(p.cf, g, 5 * sizeof(double)); }
+      break;
+    default:
+      return mmm_fail(h, MMM_ERR_ARG, "mmm_set_external_term: term is not an external term");
+  }
+  return MMM_OK;
+}
+
+int mmm_set_cutoff(mmm_handle h, double rc_nm) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, rc_nm >= 0.0 && isfinite(rc_nm), "mmm_set_cutoff: cutoff must be >= 0");
+  h->cutoff = rc_nm;
+  derive_pair_params(h);
+  return MMM_OK;
+}
+
+// ---- state -----------------------------------------------------------------------------
+static int set_center_from_host(mmm_system* h, const double* x) {
+  // arithmetic mean in index order: identical on the oracle side, so the FP32 copies agree bit for bit
+  double c[3] = {0, 0, 0};
+  for (int64_t i = 0; i < h->n; ++i)
+    for (int d = 0; d < 3; ++d) c[d] += x[3 * i + d];
+  for (int d = 0; d < 3; ++d) c[d] /= (double)h->n;
+  MMM_CUDA(h, cudaMemcpyAsync(h->d_center, c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMM_OK;
+}
+
+int mmm_set_positions(mmm_handle h, const double* xyz) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, xyz, "mmm_set_positions: NULL");
+  cudaSetDevice(h->device);
+  for (int64_t q = 0; q < 3 * h->n; ++q)
+    if (!isfinite(xyz[q])) return mmm_fail(h, MMM_ERR_NUMERIC, "mmm_set_positions: non-finite coordinate");
+  MMM_CUDA(h, cudaMemcpyAsync(h->d_x, xyz, sizeof(double) * 3 * h->n, cudaMemcpyHostToDevice, h->stream));
+  int rc = set_center_from_host(h, xyz);
+  if (rc) return rc;
+  h->positions_set = true;
+  return MMM_OK;
+}
+
+int mmm_get_positions(mmm_handle h, double* out) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, out, "mmm_get_positions: NULL");
+  REQUIRE(h, h->positions_set, "mmm_get_positions: positions were never set");
+  cudaSetDevice(h->device);
+  MMM_CUDA(h, cudaMemcpyAsync(out, h->d_x, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToHost, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMM_OK;
+}
+
+static int refresh_center_from_device(mmm_system* h) {
+  std::vector<double> x(3 * (size_t)h->n);
+  MMM_CUDA(h, cudaMemcpyAsync(x.data(), h->d_x, sizeof(double) * x.size(), cudaMemcpyDeviceToHost, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return set_center_from_host(h, x.data());
+}
+
+int mmm_set_positions_device(mmm_handle h, const double* d_xyz) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, d_xyz, "mmm_set_positions_device: NULL");
+  cudaSetDevice(h->device);
+  MMM_CUDA(h, cudaMemcpyAsync(h->d_x, d_xyz, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToDevice, h->stream));
+  int rc = refresh_center_from_device(h);
+  if (rc) return rc;
+  h->positions_set = true;
+  return MMM_OK;
+}
+
+int mmm_get_positions_device(mmm_handle h, double* d_out) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, d_out, "mmm_get_positions_device: NULL");
+  REQUIRE(h, h->positions_set, "mmm_get_positions_device: positions were never set");
+  cudaSetDevice(h->device);
+  MMM_CUDA(h, cudaMemcpyAsync(d_out, h->d_x, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToDevice, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMM_OK;
+}
+
+int mmm_hilbert_init(mmm_handle h, int p, double spacing_nm) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, p >= 1 && p <= 10, "mmm_hilbert_init: order p must be in [1, 10]");
+  REQUIRE(h, h->n <= ((int64_t)1 << (3 * p)), "mmm_hilbert_init: N exceeds the 2^(3p) points of the curve");
+  cudaSetDevice(h->device);
+  int rc = mmm_launch_hilbert(h, p, spacing_nm, nullptr);
+  if (rc) return rc;
+  if ((rc = refresh_center_from_device(h))) return rc;
+  h->positions_set = true;
+  return MMM_OK;
+}
+
+int mmm_hilbert_points(mmm_handle h, int p, int32_t* ijk_out) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, ijk_out, "mmm_hilbert_points: NULL");
+  REQUIRE(h, p >= 1 && p <= 10, "mmm_hilbert_points: order p must be in [1, 10]");
+  REQUIRE(h, h->n <= ((int64_t)1 << (3 * p)), "mmm_hilbert_points: N exceeds the 2^(3p) points of the curve");
+  cudaSetDevice(h->device);
+  int32_t* d_ijk = nullptr;
+  MMM_CUDA(h, cudaMalloc((void**)&d_ijk, sizeof(int32_t) * 3 * h->n));
+  int rc = mmm_launch_hilbert(h, p, 0.0, d_ijk);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(ijk_out, d_ijk, sizeof(int32_t) * 3 * h->n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = mmm_fail(h, MMM_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+  }
+  cudaFree(d_ijk);
+  return rc;
+}
+
+}  // extern "C"
+
+// ---- evaluation --------------------------------------------------------------------------
+static bool any_pair_term(const mmm_system* h) {
+  return h->pp.ev_form >= 0 || h->pp.cob_form >= 0 || h->pp.scb_form >= 0 || h->pp.chb_form >= 0;
+}
+
+// Size the pair-kernel work decomposition and its scratch: items = i-blocks x j-chunks, enough
+// of them that the dynamic scheduler keeps every SM busy to the end.
+static int ensure_scratch(mmm_system* h) {
+  if (h->d_fpair) return MMM_OK;
+  const int64_t niblk = h->npad / MMM_IBLOCK;
+  const int64_t stages = h->ntiles / (MMM_STAGE / MMM_TILE);
+  int64_t nchunk = 1;
+  if (any_pair_term(h)) {
+    const int64_t target = (int64_t)h->sm_count * 4 * 6;  // ~6 items per resident CTA
+    nchunk = (target + niblk - 1) / niblk;
+    nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, std::min<int64_t>(stages, 64)));
+    // chunks are whole stages; recompute the count so that no chunk is empty
+    const int64_t chunk_stages = (stages + nchunk - 1) / nchunk;
+    nchunk = (stages + chunk_stages - 1) / chunk_stages;
+  }
+  h->nchunk = (int)nchunk;
+  h->chunk_tiles = (int)((stages + nchunk - 1) / nchunk) * (MMM_STAGE / MMM_TILE);
+  h->n_items = niblk * nchunk;
+  int rc;
+  if ((rc = dev_alloc(h, &h->d_fpair, (size_t)nchunk * 3 * (size_t)h->npad))) return rc;
+  if ((rc = dev_alloc(h, &h->d_epair, (size_t)h->n_items * 4))) return rc;
+  MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * (size_t)nchunk * 3 * (size_t)h->npad, h->stream));
+  MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
+  return MMM_OK;
+}
+
+int mmm_evaluate(mmm_system* h, const int* d_skip) {
+  int rc;
+  if (h->topo_dirty && (rc = mmm_upload_topology(h))) return rc;
+  if ((rc = ensure_scratch(h))) return rc;
+  if ((rc = mmm_launch_prepare(h, d_skip))) return rc;
+  if (any_pair_term(h)) {
+    if (h->cutoff > 0.0) rc = mmm_launch_pair_cutoff(h, d_skip);
+    else rc = mmm_launch_pair_exact(h, d_skip);
+    if (rc) return rc;
+  }
+  return mmm_launch_assemble(h, d_skip);
+}
+
+static int check_ready(mmm_system* h) {
+  if (!h->positions_set) return mmm_fail(h, MMM_ERR_STATE, "positions were never set");
+  return MMM_OK;
+}
+
+// changing whether any pair term exists changes the work decomposition
+static void invalidate_scratch_if_needed(mmm_system* h) {
+  const int sig = any_pair_term(h) ? 1 : 0;
+  if (h->d_fpair && h->scratch_sig != sig) {
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_fpair); h->d_fpair = nullptr;
+    cudaFree(h->d_epair); h->d_epair = nullptr;
+  }
+  h->scratch_sig = sig;
+}
+
+extern "C" {
+
+int mmm_energy_forces_device(mmm_handle h, double* e_terms, double* d_forces) {
+  if (!h) return MMM_ERR_ARG;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  invalidate_scratch_if_needed(h);
+  if ((rc = mmm_evaluate(h, nullptr))) return rc;
+  if ((rc = mmm_launch_finalize_energy(h))) return rc;
+  double e[MMM_NUM_TERMS];
+  MMM_CUDA(h, cudaMemcpyAsync(e, h->d_eterms, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+  if (d_forces)
+    MMM_CUDA(h, cudaMemcpyAsync(d_forces, h->d_g, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToDevice, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->last_pair_ms, h->ev_a, h->ev_b);
+  double tot = 0;
+  for (int t = 0; t < MMM_NUM_TERMS; ++t) tot += e[t];
+  if (e_terms) memcpy(e_terms, e, sizeof(e));
+  if (!isfinite(tot)) return mmm_fail(h, MMM_ERR_NUMERIC, "non-finite energy");
+  return MMM_OK;
+}
+
+int mmm_energy_forces(mmm_handle h, double* e_terms, double* forces) {
+  if (!h) return MMM_ERR_ARG;
+  int rc = mmm_energy_forces_device(h, e_terms, nullptr);
+  if (rc) return rc;
+  if (forces) {
+    MMM_CUDA(h, cudaMemcpyAsync(forces, h->d_g, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int64_t q = 0; q < 3 * h->n; ++q) forces[q] = -forces[q];  // d_g holds the gradient
+  }
+  return MMM_OK;
+}
+
+int mmm_evaluate_n(mmm_handle h, int n) {
+  if (!h) return MMM_ERR_ARG;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  invalidate_scratch_if_needed(h);
+  for (int q = 0; q < n; ++q) {
+    if ((rc = mmm_evaluate(h, nullptr))) return rc;
+    if ((rc = mmm_launch_finalize_energy(h))) return rc;
+  }
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (any_pair_term(h)) cudaEventElapsedTime(&h->last_pair_ms, h->ev_a, h->ev_b);
+  return MMM_OK;
+}
+
+int mmm_minimize(mmm_handle h, double tol, int64_t max_iter, mmm_min_report* out) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, tol > 0.0 && max_iter >= 0, "mmm_minimize: tolerance must be > 0 and max_iter >= 0");
+  int rc = check_ready(h);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  invalidate_scratch_if_needed(h);
+  const size_t n3 = 3 * (size_t)h->n;
+  if (!h->d_xp) {
+    if ((rc = dev_alloc(h, &h->d_xp, n3))) return rc;
+    if ((rc = dev_alloc(h, &h->d_gp, n3))) return rc;
+    if ((rc = dev_alloc(h, &h->d_d, n3))) return rc;
+    if ((rc = dev_alloc(h, &h->d_S, n3 * MMM_LBFGS_M))) return rc;
+    if ((rc = dev_alloc(h, &h->d_Y, n3 * MMM_LBFGS_M))) return rc;
+  }
+  return mmm_run_minimize(h, tol, max_iter, out);
+}
+
+int64_t mmm_launch_count(mmm_handle h) { return h ? h->launches : 0; }
+
+int mmm_last_pair_kernel_ms(mmm_handle h, float* ms_out) {
+  if (!h || !ms_out) return MMM_ERR_ARG;
+  *ms_out = h->last_pair_ms;
+  return MMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// mmm_internal.cuh — internal declarations shared by the sm_100a translation units of
+// libmultimm_b200.so.  Not part of the public ABI (that is include/multimm_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/multimm_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// constants of the data layout
+// ---------------------------------------------------------------------------------------
+constexpr int MMM_TILE = 32;          // beads per tile (one warp's worth); bbox granularity
+constexpr int MMM_IBLOCK = 256;       // i-beads per work item of the exact pair kernel
+constexpr int MMM_STAGE = 256;        // j-beads staged in shared memory at a time
+constexpr int MMM_ASM_BLOCK = 128;    // threads per block of the O(N) assemble kernel
+constexpr int MMM_LBFGS_M = 6;        // history length (liblbfgs default used by OpenMM)
+constexpr int MMM_NDOT = 6 * MMM_LBFGS_M + 7;  // dot products per evaluation (vector-free L-BFGS)
+constexpr float MMM_PAD_COORD = 1.0e10f;       // padded beads sit here: every pair term underflows to 0
+constexpr int MMM_PAD_CHROM = 0xFFFF;
+
+// bead type bits carried in pos4.w (bit pattern of an int):
+//   [2:0]  s + 2                (sub-compartment label, model.py Cs in {-2..2})
+//   [4:3]  class: 1 = A (s > 0), 2 = B (s < 0), 3 = none (s == 0)
+//   [23:8] chromosome id (chrom_spin, model.py:158-161), 0xFFFF for padding
+__host__ __device__ inline int mmm_pack_type(int s, int chrom) {
+  int cls = s > 0 ? 1 : (s < 0 ? 2 : 3);
+  return ((s + 2) & 7) | (cls << 3) | ((chrom & 0xFFFF) << 8);
+}
+
+// ---------------------------------------------------------------------------------------
+// parameters handed to kernels by value
+// ---------------------------------------------------------------------------------------
+struct PairParams {
+  int ev_form, cob_form, scb_form, chb_form;  // MMM_FORM_OFF (-1) = absent
+  float ev_eps, ev_rs, ev_sigma, ev_power;
+  float cob_rc, cob_ea, cob_eb;
+  float scb_rc, scb_e[4];  // Ea1 (s=2), Ea2 (s=1), Eb1 (s=-1), Eb2 (s=-2)
+  float chb_kc, chb_de;
+  // derived
+  float ev_pref;    // eps * sigma^p
+  float g_c;        // -log2(e) / (2 rc^2): exp(-r^2/(2 rc^2)) = ex2(r2 * g_c)
+  float g_inv_rc2;  // 1 / rc^2
+  float rg2;        // squared range beyond which the Gaussian block terms are < 2^-40
+  float cutoff2;    // cutoff^2 (cutoff mode) or 0
+};
+
+struct ExternalParams {
+  int sc_form, lam_form, cf_form;
+  double sc[6], lam[6], cf[5];
+};
+
+// per-tile bounding box + chromosome range (2 x float4 per tile of 32 beads)
+struct __align__(16) TileInfo {
+  float lox, loy, loz;
+  int cmin;
+  float hix, hiy, hiz;
+  int cmax;
+};
+
+// L-BFGS controller state, device resident (one per handle)
+struct LbfgsState {
+  // control
+  int phase;       // 0 = idle, 1 = first evaluation pending, 2 = line search
+  int flag;        // what the next apply kernel must do (ApplyFlag)
+  int done;        // 0 running, 1 converged, 2 max_iter, 3 line-search failure, 4 non-finite
+  int ls_status;   // liblbfgs-style error code when done == 3
+  int slot;        // history slot written by the pending ACCEPT
+  int end;         // next slot to write
+  int bound;       // number of valid history pairs
+  int ls_count;
+  long long k;     // liblbfgs iteration counter (starts at 1)
+  long long iterations, evaluations, max_iter;
+  // scalars
+  double step, finit, dginit, fx, e_initial, epsilon, gnorm, xnorm;
+  double delta[2 * MMM_LBFGS_M + 1];  // coefficients of the next direction over {s_l, y_l, g}
+  double ys[MMM_LBFGS_M];
+  // Gram matrix of the stored history
+  double Gss[MMM_LBFGS_M][MMM_LBFGS_M], Gsy[MMM_LBFGS_M][MMM_LBFGS_M], Gyy[MMM_LBFGS_M][MMM_LBFGS_M];
+  double e_terms[MMM_NUM_TERMS];  // per-term energies of the most recent evaluation
+};
+
+enum ApplyFlag { APPLY_NONE = 0, APPLY_INIT = 1, APPLY_RETRY = 2, APPLY_ACCEPT = 3, APPLY_RESTORE = 4 };
+
+// ---------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------
+struct mmm_system {
+  int device = 0;
+  int64_t n = 0;       // beads
+  int64_t npad = 0;    // padded to a multiple of MMM_IBLOCK
+  int64_t ntiles = 0;  // npad / MMM_TILE
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string err;
+  int64_t launches = 0;
+
+  // parameters (host copies)
+  PairParams pp{};
+  ExternalParams ep{};
+  double cutoff = 0.0;
+  bool positions_set = false;
+  bool types_dirty = true;
+
+  // per-bead parameters
+  int* d_type = nullptr;         // packed type bits [npad]
+  double* d_cstr = nullptr;      // chrom_strength [n]
+  signed char* d_s = nullptr;    // compartment label [n]
+
+  // topology in gather (CSR) form
+  int64_t n_bonds = 0, n_loops = 0, n_angles = 0;
+  int loop_form = 0;
+  int* d_bl_ptr = nullptr;       // [n+1]
+  int* d_bl_partner = nullptr;   // [2*(nb+nl)]
+  int* d_bl_flags = nullptr;     // bit0: entry owns the energy; bits 1-2: 0 backbone bond, else 1 + loop form
+  double* d_bl_r0 = nullptr;
+  double* d_bl_k = nullptr;
+  int* d_an_ptr = nullptr;       // [n+1]
+  int4* d_an_ijk = nullptr;      // [3*na] (i, j, k, role)
+  double2* d_an_par = nullptr;   // [3*na] (theta0, k)
+  std::vector<int32_t> h_bond_i, h_bond_j, h_loop_i, h_loop_j;
+  std::vector<double> h_bond_r0, h_bond_k, h_loop_r0, h_loop_k;
+  bool topo_dirty = true;
+
+  // state
+  double* d_x = nullptr;         // [3n] master positions (nm), row-major N x 3
+  double* d_center = nullptr;    // [3] centre used for the FP32 copy
+  float4* d_pos4 = nullptr;      // [npad] centred FP32 xyz + type bits
+  TileInfo* d_tiles = nullptr;   // [ntiles]
+  double* d_g = nullptr;         // [3n] gradient (= -force)
+
+  // pair-kernel scratch
+  int nchunk = 1;
+  int chunk_tiles = 0;           // j-tiles per chunk (a whole number of stages)
+  int scratch_sig = -1;
+  double* d_fpair = nullptr;     // [nchunk][3][npad]
+  double* d_epair = nullptr;     // [items][4]
+  int64_t n_items = 0;
+  int* d_counter = nullptr;      // dynamic work counter
+
+  // reductions
+  int n_red_blocks = 0;
+  int n_dot_blocks = 0;
+  double* d_epart = nullptr;     // [n_red_blocks][6] external+bonded energy partials
+  double* d_dpart = nullptr;     // [n_red_blocks][MMM_NDOT] dot partials
+  double* d_eterms = nullptr;    // [MMM_NUM_TERMS] result of the last evaluation
+
+  // L-BFGS
+  LbfgsState* d_lb = nullptr;
+  double *d_xp = nullptr, *d_gp = nullptr, *d_d = nullptr;
+  double *d_S = nullptr, *d_Y = nullptr;  // [m][3n]
+  int* h_done = nullptr;         // pinned mirror of LbfgsState::done / counters
+
+  // cell list (cutoff mode)
+  uint32_t* d_keys = nullptr;    // [n] sorted keys
+  int* d_order = nullptr;        // [n] sorted bead order
+  uint32_t* d_keys_tmp = nullptr;
+  int* d_order_tmp = nullptr;
+  float4* d_pos4_sorted = nullptr;
+  int* d_cell_start = nullptr;   // [ncells+1]
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  int cell_dim = 0;
+  float cell_size = 0.f, cell_origin = 0.f;
+
+  // timing
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  float last_pair_ms = 0.f;
+};
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+int mmm_fail(mmm_system* h, int code, const std::string& msg);
+#define MMM_CUDA(h, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return mmm_fail((h), MMM_ERR_CUDA,                                                   \
+                      std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #call); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// kernel launchers (defined in the other .cu files)
+// ---------------------------------------------------------------------------------------
+// mmm_prepare.cu
+int mmm_launch_prepare(mmm_system* h, const int* d_skip);  // d_x -> d_pos4, d_tiles
+int mmm_launch_hilbert(mmm_system* h, int p, double spacing, int32_t* d_ijk);
+// mmm_pair.cu
+int mmm_launch_pair_exact(mmm_system* h, const int* d_skip);  // d_pos4 -> d_fpair, d_epair
+bool mmm_pair_fast_path(const mmm_system* h);
+// mmm_cells.cu
+int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip);
+// mmm_bonded.cu
+int mmm_upload_topology(mmm_system* h);
+int mmm_upload_angles(mmm_system* h, const int32_t* ai, const int32_t* aj, const int32_t* ak,
+                      const double* t0, const double* kt, int64_t na);
+int mmm_launch_assemble(mmm_system* h, const int* d_skip);  // -> d_g, d_epart
+int mmm_launch_finalize_energy(mmm_system* h);  // -> d_eterms (stand-alone evaluation)
+// mmm_lbfgs.cu
+int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report* out);
+
+// one full evaluation at the positions in d_x: prepare -> pair -> assemble.  d_skip (may be
+// NULL) points at a device flag; when it is non-zero every kernel returns immediately.
+int mmm_evaluate(mmm_system* h, const int* d_skip);

@@ -1,0 +1,136 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the CPU oracle on identical
+coordinates and parameters.  Bars (BASELINE.json north_star): per-term energies 1e-5 relative,
+per-bead forces 1e-4 relative, topology / integer outputs bit-exact."""
+import numpy as np
+import pytest
+
+from common import O, force_rel_err, make_case, to_engine, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-5
+F_TOL = 1e-4
+
+
+def _fp32_positions(case):
+    """Both sides see the same coordinates: the engine's FP32 copy is exact for these values."""
+    c = case["x"].mean(axis=0)
+    case["x"] = (case["x"] - c).astype(np.float32).astype(np.float64) + c
+    return case
+
+
+def _check(case, e_tol=E_TOL, f_tol=F_TOL):
+    eng = to_engine(case)
+    e, f = eng.energy_forces()
+    e_ref, f_ref = O.energy_forces(to_oracle(case), case["x"])
+    for t in range(10):
+        scale = max(abs(e_ref[t]), 1e-12)
+        assert abs(e[t] - e_ref[t]) <= e_tol * scale + 1e-9, (O.TERM_NAMES[t], e[t], e_ref[t])
+    err = force_rel_err(f, f_ref)
+    assert err <= f_tol, err
+    eng.close()
+    return e, f
+
+
+@pytest.mark.parametrize("n,n_chrom", [(1000, 1), (2500, 3), (10000, 5)])
+def test_all_default_terms(built_lib, n, n_chrom):
+    _check(make_case(n, n_chrom=n_chrom, seed=n))
+
+
+def test_s1_region_terms(built_lib):
+    """configs[0]: specific-region model, {bonds, angles, loops, EV}."""
+    _check(make_case(10000, terms=("EV", "BOND", "LOOP", "ANGLE"), seed=3))
+
+
+def test_cob_and_scb_together(built_lib):
+    _check(make_case(3000, n_chrom=2, terms=("EV", "COB", "SCB", "BOND", "ANGLE"), seed=4))
+
+
+def test_cob_only(built_lib):
+    _check(make_case(3000, n_chrom=2, terms=("EV", "COB", "CHB"), seed=5))
+
+
+def test_ragged_sizes(built_lib):
+    for n in (2, 3, 31, 33, 255, 257, 1023):
+        terms = ("EV", "SCB", "CHB", "SC", "LAM", "CF", "BOND", "ANGLE") if n >= 40 else ("EV", "SCB", "CHB", "SC", "LAM", "CF")
+        case = make_case(n, n_chrom=1 if n < 40 else 2, seed=n, terms=terms)
+        _check(case)
+
+
+def test_ev_power_3(built_lib):
+    _check(make_case(2000, terms=("EV", "BOND"), ev_power=3.0, seed=6))
+
+
+def test_generic_forms(built_lib):
+    """Non-default functional forms go through the generic pair path (model.py alternates)."""
+    for forms in ({"EV": 1}, {"COB": 1, "SCB": 1}, {"COB": 2, "SCB": 2}, {"CHB": 1}, {"CHB": 2},
+                  {"LAM": 1, "CF": 1, "LOOP": 1}, {"LAM": 2, "CF": 2, "LOOP": 2}, {"LAM": 3}):
+        case = make_case(1500, n_chrom=3, seed=11, forms=forms, chb_de=1.0,
+                         terms=("EV", "COB", "SCB", "CHB", "SC", "LAM", "CF", "BOND", "LOOP", "ANGLE"))
+        _check(case, e_tol=3e-5, f_tol=2e-4)
+
+
+def test_non_integer_ev_power(built_lib):
+    _check(make_case(1500, terms=("EV",), ev_power=4.5, seed=7), e_tol=3e-5, f_tol=2e-4)
+
+
+def test_hilbert_bit_exact(built_lib):
+    from multimm_b200.engine import Engine
+
+    for n in (8, 4096, 100000):
+        eng = Engine(n)
+        pts = eng.hilbert_points(8)
+        assert np.array_equal(pts, O.hilbert_points(n, 8))
+        eng.hilbert_init(8, 0.1)
+        assert np.array_equal(eng.get_positions(), pts.astype(np.float64) * 0.1)
+        eng.close()
+
+
+def test_determinism_and_newton(built_lib):
+    case = make_case(5000, n_chrom=4, seed=9, terms=("EV", "SCB", "CHB"))
+    eng = to_engine(case)
+    e1, f1 = eng.energy_forces()
+    e2, f2 = eng.energy_forces()
+    assert np.array_equal(e1, e2) and np.array_equal(f1, f2)
+    # pair forces sum to zero (Newton's third law) to FP32 accumulation accuracy
+    assert np.abs(f1.sum(axis=0)).max() < 1e-3 * np.abs(f1).max()
+    eng.close()
+
+
+def test_translation_invariance(built_lib):
+    case = make_case(4000, n_chrom=2, seed=10, terms=("EV", "SCB", "CHB", "BOND", "ANGLE", "LOOP"))
+    eng = to_engine(case)
+    e1, _ = eng.energy_forces()
+    eng.set_positions(case["x"] + np.array([3.0, -2.0, 1.0]))
+    e2, _ = eng.energy_forces()
+    assert np.allclose(e1, e2, rtol=2e-6, atol=1e-6)
+    eng.close()
+
+
+def test_minimize_matches_oracle_energy(built_lib):
+    """Final minimised energy within 1e-3 relative of the CPU L-BFGS (trajectories are chaotic)."""
+    case = make_case(600, n_chrom=2, seed=12, noise=0.0)
+    eng = to_engine(case)
+    rep = eng.minimize(tol=10.0, max_iter=0)
+    x_ref, rep_ref = O.minimize(to_oracle(case), case["x"], tol=10.0, max_iter=0)
+    assert rep["converged"] == 1 and rep_ref["converged"] == 1, (rep, rep_ref)
+    assert rep["e_final"] < rep["e_initial"]
+    # the engine's own final energy agrees with the oracle evaluated at the engine's positions
+    e_chk = O.energy_forces(to_oracle(case), eng.get_positions(), want_forces=False)[0].sum()
+    assert abs(e_chk - rep["e_final"]) <= 1e-5 * abs(e_chk)
+    assert abs(rep["e_final"] - rep_ref["e_final"]) <= 1e-3 * abs(rep_ref["e_final"]), (rep, rep_ref)
+    assert rep["rms_force"] <= 10.0 * 1.0001
+    eng.close()
+
+
+def test_errors(built_lib):
+    from multimm_b200.engine import Engine, Error
+
+    eng = Engine(100)
+    with pytest.raises(Error):
+        eng.energy_forces()  # positions never set
+    with pytest.raises(ValueError):
+        eng.set_pair_term("EV", 7, [1, 2, 3, 4])  # unknown form -> ValueError like model.py:213-215
+    with pytest.raises(ValueError):
+        eng.set_loops([0], [5], [0.1], [1.0], form=9)
+    eng.close()
