@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — force evaluations per second of the genome-wide MultiMM model on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload gw|chrom|region]
+
+Metric (BASELINE.json: "genome-wide minimization wall-time; force evals/s; ..."): combined
+energy+force evaluations per second of the genome-wide system (N = 2e5 beads, flags of
+examples/config_gw.ini).  A step is ONE fused evaluation of every term (prepare -> exact
+all-pairs kernel -> bonded/external pass -> energy reduction) — the thing OpenMM does once per
+L-BFGS line-search trial.  The workload is built the way a user builds it: synthetic .bedpe/.bed
+files in the reference's formats -> loaders -> MultiMM.add_* -> engine (C-ABI).
+
+`value`  : inputs resident in HBM, K evaluations timed with CUDA events on the engine's stream.
+`e2e`    : the same evaluation through the C-ABI with HOST buffers: positions copied host->device
+           and forces device->host every step (what LocalEnergyMinimizer does per evaluation).
+`roofline`: the exact pair kernel against the FP32-FMA peak measured in this run by an FFMA
+           micro-benchmark (MEASURED_PEAKS.json carries only HBM and bf16; this kernel is bound by
+           FP32/MUFU issue, not by HBM or tensor cores).  Algorithmic flops: SURVEY.md 8(d).
+`cpu_baseline`: the CPU oracle (FP64 restatement of the OpenMM Reference semantics, OpenMP) on a
+           bounded sample of the same system.  OpenMM itself is not installable in this image.
+N > 1 (torchrun): one independent replica per GPU (ensemble members, seeds = rank), no data-path
+collective; value = evaluations of all ranks / max-over-ranks device time; scaling "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (synthetic config key, flags)
+    "gw": dict(key="S3_gw", n_beads=200_000, chrom=None, region=None, n_loops=10_000,
+               flags=dict(SC_USE_SPHERICAL_CONTAINER=True, CHB_USE_CHROMOSOMAL_BLOCKS=True,
+                          SCB_USE_SUBCOMPARTMENT_BLOCKS=True, IBL_USE_B_LAMINA_INTERACTION=True,
+                          CF_USE_CENTRAL_FORCE=True, COB_USE_COMPARTMENT_BLOCKS=False, SHUFFLE_CHROMS=True),
+               name="genome-wide, N=200000, 22 chromosomes, EV+SCB+CHB+SC+LAM+CF+bonds+loops+angles "
+                    "(examples/config_gw.ini flags), exact all-pairs"),
+    "chrom": dict(key="S2_chrom", n_beads=50_000, chrom="chr1", region=None, n_loops=2_000,
+                  flags=dict(SCB_USE_SUBCOMPARTMENT_BLOCKS=True),
+                  name="single chromosome chr1, N=50000, EV+SCB+bonds+loops+angles, exact all-pairs"),
+    "region": dict(key="S1_region", n_beads=10_000, chrom="chr1", region=(10_000_000, 110_000_000), n_loops=400,
+                   flags=dict(), name="specific region chr1:10-110Mb, N=10000, EV+bonds+loops+angles, exact all-pairs"),
+}
+
+
+def build_model(workload: str, seed: int, device: int, tmp: str, with_engine: bool = True):
+    """Synthetic input files -> SimulationConfig -> MultiMM with its force field on the device."""
+    from multimm_b200 import synthetic
+    from multimm_b200.config import SimulationConfig
+    from multimm_b200.model import MultiMM
+
+    w = WORKLOADS[workload]
+    bedpe = os.path.join(tmp, f"loops_{seed}.bedpe")
+    bed = os.path.join(tmp, f"comps_{seed}.bed")
+    synthetic.write_bedpe(bedpe, n_loops=w["n_loops"], seed=100 + seed, chrom=w["chrom"], region=w["region"])
+    synthetic.write_bed(bed, seed=100 + seed, chrom=w["chrom"])
+    kw = dict(PLATFORM="B200", N_BEADS=w["n_beads"], LOOPS_PATH=bedpe, COMPARTMENT_PATH=bed,
+              OUT_PATH=os.path.join(tmp, f"out_{seed}"), SHUFFLING_SEED=seed, SAVE_PLOTS=False, **w["flags"])
+    if w["chrom"]:
+        kw["CHROM"] = w["chrom"]
+    if w["region"]:
+        kw["LOC_START"], kw["LOC_END"] = w["region"]
+    args = SimulationConfig(**kw)
+    m = MultiMM(args, device=device)
+    m.set_radiuses()
+    if with_engine:
+        m.initialize_simulation()
+        m.add_forcefield()
+    return m
+
+
+def oracle_system(m, n_sub: int):
+    """The first n_sub beads of the model as an oracle System (same parameters, same start)."""
+    from multimm_b200 import structures
+    from multimm_b200.model import _f, backbone_angles, backbone_bonds
+    from oracle import oracle as O
+
+    a = m.args
+    n = a.N_BEADS
+    x = structures.hilbert_points_host(n, 8).astype(np.float64) * 0.1
+    center = x.mean(axis=0)
+    sub = slice(0, n_sub)
+    bi = backbone_bonds(n, m.chr_ends)
+    bi = bi[bi + 1 < n_sub]
+    ai = backbone_angles(n, m.chr_ends)
+    ai = ai[ai + 2 < n_sub]
+    keep = np.asarray(m.ns) < n_sub
+    lm, ln, lr0 = np.asarray(m.ms)[keep], np.asarray(m.ns)[keep], np.asarray(m.ds)[keep]
+    s = np.zeros(n, dtype=np.int8) if m.Cs is None else np.asarray(m.Cs, dtype=np.int8)
+    sysd = O.System(
+        n=n_sub,
+        ev=(0, [a.EV_EPSILON, a.EV_R_SMALL, _f(a.LE_HARMONIC_BOND_R0), a.EV_POWER]) if a.EV_USE_EXCLUDED_VOLUME else None,
+        cob=(0, [m.r_comp, a.COB_EA, a.COB_EB]) if a.COB_USE_COMPARTMENT_BLOCKS else None,
+        scb=(0, [m.r_comp, a.SCB_EA1, a.SCB_EA2, a.SCB_EB1, a.SCB_EB2]) if a.SCB_USE_SUBCOMPARTMENT_BLOCKS else None,
+        chb=(0, [a.CHB_KC, a.CHB_DE]) if a.CHB_USE_CHROMOSOMAL_BLOCKS else None,
+        sc=(0, [a.SC_SCALE, m.radius1, m.radius2, *center]) if a.SC_USE_SPHERICAL_CONTAINER else None,
+        lam=(0, [a.IBL_SCALE, m.radius1, m.radius2, *center]) if a.IBL_USE_B_LAMINA_INTERACTION else None,
+        cf=(0, [a.CF_STRENGTH, m.radius1, *center]) if a.CF_USE_CENTRAL_FORCE else None,
+        s=s[sub], chrom=m.chrom_spin[sub].astype(np.int32), cstr=m.chrom_strength[sub],
+        bonds=(bi, bi + 1, np.full(len(bi), _f(a.POL_HARMONIC_BOND_R0)), np.full(len(bi), _f(a.POL_HARMONIC_BOND_K))),
+        loops=(lm, ln, lr0, np.full(len(lm), _f(a.LE_HARMONIC_BOND_K))),
+        angles=(ai, ai + 1, ai + 2, np.full(len(ai), _f(a.POL_HARMONIC_ANGLE_R0)),
+                np.full(len(ai), _f(a.POL_HARMONIC_ANGLE_CONSTANT_K))),
+    )
+    return sysd, x[sub].copy()
+
+
+def cpu_baseline(m, target_seconds: float = 12.0, reps: int = 1):
+    """Oracle timed on all host cores on a bounded sample; extrapolated to the full system by
+    pair count (the O(N^2) pair loop is > 99.9 % of the oracle's time)."""
+    from oracle import oracle as O
+
+    n = m.args.N_BEADS
+    cores = os.cpu_count() or 1
+    sysd, x = oracle_system(m, min(n, 6000))
+    O.energy_forces(sysd, x)  # warm
+    t0 = time.perf_counter()
+    O.energy_forces(sysd, x)
+    probe = time.perf_counter() - t0
+    rate = (sysd.n * (sysd.n - 1) / 2) / max(probe, 1e-9)  # pairs/s
+    n_sub = int(min(n, max(6000, np.sqrt(2.0 * rate * target_seconds / max(reps, 1)))))
+    sysd, x = oracle_system(m, n_sub)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.energy_forces(sysd, x)
+    dt = (time.perf_counter() - t0) / reps
+    pairs_sub = n_sub * (n_sub - 1) / 2
+    pairs_full = n * (n - 1) / 2
+    evals_per_s = (pairs_sub / dt) / pairs_full
+    return dict(value=evals_per_s, unit="force_evals/s", cores=cores, kind="port",
+                sample=f"CPU oracle (FP64 restatement of OpenMM Reference semantics, OpenMP x{cores}) on the first "
+                       f"{n_sub} beads of the same system ({pairs_sub:.3g} pairs in {dt:.2f} s), scaled to "
+                       f"{pairs_full:.3g} pairs; OpenMM itself is not installable here (no wheel, no network)",
+                pairs_per_s=pairs_sub / dt, sample_beads=n_sub, sample_seconds=dt)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines: list[str] = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.kill()  # exact PID we started
+            self.proc.wait()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def pair_flops(m) -> tuple[float, float]:
+    """Algorithmic flops of one evaluation of the pair kernel: per unordered pair
+    16 (geometry + accumulation) + (body + 2) per active term: EV power-law 12, each Gaussian block
+    term 6, CHB polynomial 12 charged on same-chromosome pairs only.  Returns (flops, pairs)."""
+    a = m.args
+    n = a.N_BEADS
+    pairs = n * (n - 1) / 2.0
+    per = 16.0
+    if a.EV_USE_EXCLUDED_VOLUME:
+        per += 12.0
+    per += 6.0 * (bool(a.COB_USE_COMPARTMENT_BLOCKS) + bool(a.SCB_USE_SUBCOMPARTMENT_BLOCKS))
+    flops = pairs * per
+    if a.CHB_USE_CHROMOSOMAL_BLOCKS:
+        sizes = np.diff(np.asarray(m.chr_ends)).astype(np.float64)
+        flops += 12.0 * float((sizes * (sizes - 1) / 2.0).sum())
+    return flops, pairs
+
+
+def run_ours(opt):
+    import torch
+    import torch.distributed as dist
+
+    from multimm_b200.engine import measure_fp32_peak
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    K, W = opt.steps, max(opt.warmup, 3)
+    w = WORKLOADS[opt.workload]
+
+    with tempfile.TemporaryDirectory(prefix="mmm_bench_") as tmp:
+        t_build0 = time.perf_counter()
+        m = build_model(opt.workload, seed=rank, device=local, tmp=tmp)
+        eng = m.engine
+        build_s = time.perf_counter() - t_build0
+        n = m.args.N_BEADS
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- device-resident: K evaluations, CUDA events on the engine's stream -----------------
+        eng.evaluate_timed(W, flush_l2=True)
+        launches0 = eng.launch_count
+        barrier()
+        with ClockSampler(local) as clk:
+            total_ms, pair_ms = eng.evaluate_timed(K, flush_l2=True)
+            barrier()
+        launches = eng.launch_count - launches0
+        t = torch.tensor([total_ms, pair_ms], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, pair_ms_max = float(t[0]), float(t[1])
+        value = world * K / (total_ms * 1e-3)
+
+        # ---- end to end through the C-ABI with host buffers ------------------------------------
+        x_host = torch.from_numpy(m.positions.copy()).pin_memory()
+        x_np = x_host.numpy()
+        for _ in range(2):
+            eng.set_positions(x_np)
+            eng.energy_forces()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            eng.set_positions(x_np)
+            e_terms, forces = eng.energy_forces()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * K / float(t[0])
+
+        if rank != 0:
+            m.close()
+            if world > 1:
+                dist.destroy_process_group()
+            return
+
+        # ---- rank 0 only: roofline, CPU baseline, a bounded minimisation ------------------------
+        flops, pairs = pair_flops(m)
+        peak_tflops, mufu_tops = measure_fp32_peak(local)
+        pair_ms_avg = pair_ms / K
+        achieved = flops / (pair_ms_avg * 1e-3) / 1e12
+        roofline = dict(
+            bound="fp32", kernel="k_pair_exact", achieved=achieved, peak=peak_tflops, unit="TFLOP/s",
+            frac=achieved / peak_tflops if peak_tflops > 0 else None, traffic=None,
+            peak_source="FFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP32 entry); "
+                        f"MUFU peak measured likewise: {mufu_tops:.2f} Tera-op/s",
+            algorithmic_flops_per_launch=flops, unordered_pairs_per_launch=pairs,
+            pair_kernel_ms=pair_ms_avg, pairs_per_s=pairs / (pair_ms_avg * 1e-3),
+            kernel_share_of_step=pair_ms / total_ms)
+        base = None
+        if world == 1 and not opt.no_cpu:
+            base = cpu_baseline(m, target_seconds=opt.cpu_seconds)
+        mini = None
+        if opt.minimize_iters > 0 and world == 1:
+            eng.set_positions(x_np)
+            rep = eng.minimize(tol=10.0, max_iter=opt.minimize_iters)
+            mini = dict(max_iter=opt.minimize_iters, **rep)
+        out = dict(
+            metric="force_evals_per_s", value=value, unit="force_evals/s", n_gpus=world, steps=K, warmup=W,
+            ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+            data="synthetic",
+            config=dict(workload=w["name"], n_beads=n, n_loops=int(len(m.ms)), n_bonds=int(m.n_bonds),
+                        n_angles=int(m.n_angles), replicas=world, l2="flushed between steps (256 MiB memset inside "
+                        "the timed region)", start="Hilbert lattice (0.1 nm)", build_seconds=build_s),
+            clocks=clk.summary(),
+            e2e=dict(value=e2e_value, unit="force_evals/s", h2d_bytes_per_step=24 * n,
+                     d2h_bytes_per_step=24 * n + 8 * len(e_terms)),
+            gpu_launches=int(launches),
+            roofline=roofline, cpu_baseline=base, minimize=mini,
+            energy_terms={k: float(v) for k, v in zip(("EV", "COB", "SCB", "CHB", "SC", "LAM", "CF", "BOND", "LOOP",
+                                                        "ANGLE"), e_terms)},
+        )
+        print(json.dumps(out), flush=True)
+        m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(opt):
+    """The reference arm: OpenMM cannot be installed here, so the reference's CPU implementation is
+    represented by the oracle port on all host cores; each step is a bounded sample."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    K, W = opt.steps, opt.warmup
+    w = WORKLOADS[opt.workload]
+    with tempfile.TemporaryDirectory(prefix="mmm_bench_ref_") as tmp:
+        m = build_model(opt.workload, seed=0, device=0, tmp=tmp, with_engine=False)
+        budget = max(1.0, min(opt.cpu_seconds, 150.0 / max(K + W, 1)))
+        for _ in range(W):
+            base = cpu_baseline(m, target_seconds=budget)
+        vals = []
+        t0 = time.perf_counter()
+        for _ in range(K):
+            base = cpu_baseline(m, target_seconds=budget)
+            vals.append(base["value"])
+        wall = time.perf_counter() - t0
+        value = float(np.mean(vals))
+        out = dict(
+            impl="reference", metric="force_evals_per_s", value=value, unit="force_evals/s",
+            n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=K, warmup=W, ms_per_step=1e3 / value,
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=w["name"], n_beads=m.args.N_BEADS, note="each step times a bounded sample and scales "
+                        "by pair count; ms_per_step is the extrapolated time of one full evaluation"),
+            cpu_baseline=dict(base, value=value),
+            e2e=dict(value=value, unit="force_evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+            gpu_launches=0, wall_seconds=wall)
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="gw", choices=tuple(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--minimize-iters", type=int, default=50)
+    opt = ap.parse_args()
+    if opt.impl == "reference":
+        run_reference(opt)
+    else:
+        run_ours(opt)
+
+
+if __name__ == "__main__":
+    main()

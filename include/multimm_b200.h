@@ -161,6 +161,12 @@ int mmm_energy_forces_device(mmm_handle h, double *e_terms, double *d_forces /* 
 /* Launch `n` evaluations back to back without host synchronisation in between (bench). */
 int mmm_evaluate_n(mmm_handle h, int n);
 
+/* `n` evaluations timed with CUDA events on the handle's own stream (where the kernels are
+ * launched).  flush_l2 != 0 overwrites a 256 MiB scratch buffer before every evaluation, inside
+ * the timed region.  total_ms: all n evaluations (flushes included); pair_ms: sum of the n pair
+ * kernel launches alone (per-launch events). Either output may be NULL. */
+int mmm_evaluate_timed(mmm_handle h, int n, int flush_l2, float *total_ms, float *pair_ms);
+
 /* ---- minimisation (Simulation.minimizeEnergy(), model.py:886) -------------------- */
 /* L-BFGS (m = 6, strong-Wolfe backtracking) until the per-particle RMS-force rule of
  * OpenMM's LocalEnergyMinimizer is met: |g| / max(1,|x|) < tol / max(1, rms|x_i|).

@@ -31,7 +31,7 @@ EXPORTS = (
     "mmm_set_pair_term", "mmm_set_external_term", "mmm_set_cutoff",
     "mmm_set_positions", "mmm_get_positions", "mmm_set_positions_device", "mmm_get_positions_device",
     "mmm_hilbert_init", "mmm_hilbert_points",
-    "mmm_energy_forces", "mmm_energy_forces_device", "mmm_evaluate_n", "mmm_minimize",
+    "mmm_energy_forces", "mmm_energy_forces_device", "mmm_evaluate_n", "mmm_evaluate_timed", "mmm_minimize",
     "mmm_launch_count", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_measure_fp32_peak",
 )
 
@@ -88,6 +88,7 @@ def load():
         "mmm_energy_forces": (i32, [vp, vp, vp]),
         "mmm_energy_forces_device": (i32, [vp, vp, vp]),
         "mmm_evaluate_n": (i32, [vp, i32]),
+        "mmm_evaluate_timed": (i32, [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "mmm_minimize": (i32, [vp, dbl, i64, C.POINTER(MinReport)]),
         "mmm_launch_count": (i64, [vp]),
         "mmm_last_pair_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),

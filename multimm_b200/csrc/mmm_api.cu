@@ -128,6 +128,8 @@ int mmm_destroy(mmm_handle h) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_done) cudaFreeHost(h->h_done);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->d_flush) cudaFree(h->d_flush);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -486,6 +488,48 @@ int mmm_evaluate_n(mmm_handle h, int n) {
   }
   MMM_CUDA(h, cudaStreamSynchronize(h->stream));
   if (any_pair_term(h)) cudaEventElapsedTime(&h->last_pair_ms, h->ev_a, h->ev_b);
+  return MMM_OK;
+}
+
+int mmm_evaluate_timed(mmm_handle h, int n, int flush_l2, float* total_ms, float* pair_ms) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, n >= 1 && n <= 100000, "mmm_evaluate_timed: n must be in [1, 100000]");
+  int rc = check_ready(h);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  invalidate_scratch_if_needed(h);
+  const size_t flush_bytes = (size_t)256 << 20;
+  if (flush_l2 && !h->d_flush) MMM_CUDA(h, cudaMalloc(&h->d_flush, flush_bytes));
+  while (h->ev_pool.size() < (size_t)2 * n + 2) {
+    cudaEvent_t e;
+    MMM_CUDA(h, cudaEventCreate(&e));
+    h->ev_pool.push_back(e);
+  }
+  // the last two pool events bracket the whole batch
+  cudaEvent_t t0 = h->ev_pool[h->ev_pool.size() - 2], t1 = h->ev_pool[h->ev_pool.size() - 1];
+  h->ev_cursor = any_pair_term(h) ? 0 : -1;
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  MMM_CUDA(h, cudaEventRecord(t0, h->stream));
+  for (int q = 0; q < n; ++q) {
+    if (flush_l2) MMM_CUDA(h, cudaMemsetAsync(h->d_flush, q & 0xff, flush_bytes, h->stream));
+    if ((rc = mmm_evaluate(h, nullptr))) { h->ev_cursor = -1; return rc; }
+    if ((rc = mmm_launch_finalize_energy(h))) { h->ev_cursor = -1; return rc; }
+  }
+  MMM_CUDA(h, cudaEventRecord(t1, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int collected = h->ev_cursor;
+  h->ev_cursor = -1;
+  float tot = 0.f, pair = 0.f;
+  cudaEventElapsedTime(&tot, t0, t1);
+  for (int q = 0; q < collected; ++q) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_pool[2 * q], h->ev_pool[2 * q + 1]);
+    pair += ms;
+  }
+  if (collected > 0) h->last_pair_ms = pair / collected;
+  if (total_ms) *total_ms = tot;
+  if (pair_ms) *pair_ms = pair;
+  MMM_CUDA(h, cudaGetLastError());
   return MMM_OK;
 }
 

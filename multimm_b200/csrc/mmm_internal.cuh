@@ -168,6 +168,9 @@ struct mmm_system {
 
   // timing
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  std::vector<cudaEvent_t> ev_pool;  // per-launch event pairs while a timed batch runs
+  int ev_cursor = -1;                // -1: not collecting
+  void* d_flush = nullptr;           // 256 MiB L2-flush scratch (bench only)
   float last_pair_ms = 0.f;
 };
 

@@ -447,7 +447,11 @@ int mmm_launch_pair_exact(mmm_system* h, const int* d_skip) {
   A.n_items = (int)h->n_items;
   A.pp = h->pp;
   MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
-  MMM_CUDA(h, cudaEventRecord(h->ev_a, h->stream));
+  const bool collect = h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
+  cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
+  cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
+  if (collect) h->ev_cursor++;
+  MMM_CUDA(h, cudaEventRecord(ea, h->stream));
   if (mmm_pair_fast_path(h)) {
     const int gk = (h->pp.scb_form >= 0 ? 1 : 0) | (h->pp.cob_form >= 0 ? 2 : 0);
     const bool chb = h->pp.chb_form >= 0;
@@ -458,6 +462,6 @@ int mmm_launch_pair_exact(mmm_system* h, const int* d_skip) {
   }
   h->launches++;
   MMM_CUDA(h, cudaGetLastError());
-  MMM_CUDA(h, cudaEventRecord(h->ev_b, h->stream));
+  MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
 }

@@ -149,6 +149,12 @@ class Engine:
     def evaluate_n(self, n: int):
         self._ck(self._lib.mmm_evaluate_n(self._h, int(n)))
 
+    def evaluate_timed(self, n: int, flush_l2: bool = True):
+        """n evaluations timed on the device; returns (total_ms, summed pair-kernel ms)."""
+        tot, pair = C.c_float(), C.c_float()
+        self._ck(self._lib.mmm_evaluate_timed(self._h, int(n), int(bool(flush_l2)), C.byref(tot), C.byref(pair)))
+        return float(tot.value), float(pair.value)
+
     def minimize(self, tol: float = 10.0, max_iter: int = 0) -> dict:
         """L-BFGS to OpenMM's default tolerance (10 kJ/mol/nm RMS force), unlimited iterations."""
         rep = MinReport()

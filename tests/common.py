@@ -54,7 +54,7 @@ def make_case(n, n_chrom=1, seed=0, terms=("EV", "SCB", "CHB", "SC", "LAM", "CF"
     r1, r2, r_comp = radii(n)
     # chromosome boundaries (chr_ends = [0, e1, ..., N])
     if n_chrom > 1:
-        cuts = np.sort(rng.choice(np.arange(8, n - 8), size=n_chrom - 1, replace=False))
+        cuts = np.sort(rng.choice(np.arange(3, n - 3), size=n_chrom - 1, replace=False))
         chr_ends = np.concatenate([[0], cuts, [n]])
     else:
         chr_ends = np.array([0, n])
@@ -76,10 +76,13 @@ def make_case(n, n_chrom=1, seed=0, terms=("EV", "SCB", "CHB", "SC", "LAM", "CF"
     center = x.mean(axis=0)
     bi, ai = backbone(n, chr_ends)
     nl = n_loops if n_loops is not None else max(1, n // 25)
-    lm = rng.integers(0, n - 4, size=nl)
-    ln = np.minimum(lm + 3 + rng.geometric(1.0 / 30.0, size=nl), n - 1)
-    keep = ln > lm + 2
-    lm, ln = lm[keep].astype(np.int32), ln[keep].astype(np.int32)
+    if n > 8:
+        lm = rng.integers(0, n - 4, size=nl)
+        ln = np.minimum(lm + 3 + rng.geometric(1.0 / 30.0, size=nl), n - 1)
+        keep = ln > lm + 2
+        lm, ln = lm[keep].astype(np.int32), ln[keep].astype(np.int32)
+    else:
+        lm = ln = np.zeros(0, dtype=np.int32)
     lr0 = 0.1 + 0.1 * rng.random(len(lm))
     case = dict(n=n, x=x, s=s, chrom=chrom, cstr=cstr, chr_ends=chr_ends, center=center,
                 r1=r1, r2=r2, r_comp=r_comp, terms=tuple(terms), forms=forms)
