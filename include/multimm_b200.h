@@ -176,6 +176,11 @@ int mmm_minimize(mmm_handle h, double tol_kj_mol_nm, int64_t max_iter, mmm_min_r
 /* ---- introspection (tests, bench) ---------------------------------------------------- */
 /* Number of kernels this handle has launched since creation. */
 int64_t mmm_launch_count(mmm_handle h);
+/* Pair-kernel selection (tests, A/B timing): 0 = automatic (Newton-3 kernel for the reference's
+ * default forms, gather kernel otherwise), 1 = always the gather kernel. */
+int mmm_set_pair_kernel(mmm_handle h, int which);
+/* Kernel the last evaluation used: 0 none, 1 gather, 2 Newton-3, 3 cut-off cell list. */
+int mmm_pair_kernel_in_use(mmm_handle h);
 /* Time of the most recent mmm_evaluate_n / mmm_energy_forces pair kernel, ms (CUDA events
  * on the handle's stream). */
 int mmm_last_pair_kernel_ms(mmm_handle h, float *ms_out);

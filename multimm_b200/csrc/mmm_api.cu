@@ -73,7 +73,7 @@ int mmm_create(int device, int64_t n_beads, mmm_handle* out) {
   if (!h) return mmm_fail(nullptr, MMM_ERR_NOMEM, "out of host memory");
   h->device = device;
   h->n = n_beads;
-  h->npad = (n_beads + MMM_IBLOCK - 1) / MMM_IBLOCK * MMM_IBLOCK;
+  h->npad = (n_beads + MMM_PAD_TO - 1) / MMM_PAD_TO * MMM_PAD_TO;
   h->ntiles = h->npad / MMM_TILE;
   h->sm_count = prop.multiProcessorCount;
   h->pp.ev_form = h->pp.cob_form = h->pp.scb_form = h->pp.chb_form = MMM_FORM_OFF;
@@ -106,8 +106,9 @@ int mmm_create(int device, int64_t n_beads, mmm_handle* out) {
   cudaMemsetAsync(h->d_cstr, 0, sizeof(double) * n_beads, h->stream);
   cudaMemsetAsync(h->d_s, 0, n_beads, h->stream);
   cudaMemsetAsync(h->d_lb, 0, sizeof(LbfgsState), h->stream);
-  std::vector<int> ty((size_t)h->npad, mmm_pack_type(0, MMM_PAD_CHROM));
-  for (int64_t i = 0; i < n_beads; ++i) ty[i] = mmm_pack_type(0, 0);
+  std::vector<int> ty((size_t)h->npad);
+  for (int64_t i = 0; i < h->npad; ++i)
+    ty[i] = i < n_beads ? mmm_pack_type(0, 0) : mmm_pack_type(0, MMM_PAD_CHROM + (int)(i - n_beads));
   cudaMemcpyAsync(h->d_type, ty.data(), sizeof(int) * ty.size(), cudaMemcpyHostToDevice, h->stream);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess)
     return fail(mmm_fail(h, MMM_ERR_CUDA, "CUDA error: initialisation copies failed"));
@@ -122,7 +123,7 @@ int mmm_destroy(mmm_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_type, h->d_cstr, h->d_s, h->d_bl_ptr, h->d_bl_partner, h->d_bl_flags, h->d_bl_r0, h->d_bl_k,
                   h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_tiles, h->d_g,
-                  h->d_fpair, h->d_epair, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
+                  h->d_fpair, h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
                   h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp};
   for (void* p : ptrs)
@@ -187,13 +188,14 @@ int mmm_set_angles(mmm_handle h, const int32_t* i, const int32_t* j, const int32
 int mmm_set_bead_params(mmm_handle h, const int8_t* s, const int32_t* chrom, const double* chrom_strength) {
   if (!h) return MMM_ERR_ARG;
   cudaSetDevice(h->device);
-  std::vector<int> ty((size_t)h->npad, mmm_pack_type(0, MMM_PAD_CHROM));
+  std::vector<int> ty((size_t)h->npad);
+  for (int64_t i = h->n; i < h->npad; ++i) ty[i] = mmm_pack_type(0, MMM_PAD_CHROM + (int)(i - h->n));
   std::vector<signed char> sv((size_t)h->n, 0);
   for (int64_t i = 0; i < h->n; ++i) {
     const int si = s ? (int)s[i] : 0;
     const int ci = chrom ? chrom[i] : 0;
     if (si < -2 || si > 2) return mmm_fail(h, MMM_ERR_ARG, "mmm_set_bead_params: compartment label outside [-2, 2]");
-    if (ci < 0 || ci >= MMM_PAD_CHROM) return mmm_fail(h, MMM_ERR_ARG, "mmm_set_bead_params: chromosome id outside [0, 65534]");
+    if (ci < 0 || ci >= MMM_PAD_CHROM) return mmm_fail(h, MMM_ERR_ARG, "mmm_set_bead_params: chromosome id outside [0, 64511]");
     ty[i] = mmm_pack_type(si, ci);
     sv[i] = (signed char)si;
   }
@@ -386,29 +388,71 @@ static bool any_pair_term(const mmm_system* h) {
   return h->pp.ev_form >= 0 || h->pp.cob_form >= 0 || h->pp.scb_form >= 0 || h->pp.chb_form >= 0;
 }
 
-// Size the pair-kernel work decomposition and its scratch: items = i-blocks x j-chunks, enough
-// of them that the dynamic scheduler keeps every SM busy to the end.
+// Which pair kernel serves the current parameters.
+static int wanted_pair_mode(const mmm_system* h) {
+  if (!any_pair_term(h)) return 0;
+  if (h->cutoff > 0.0) return 3;
+  if (h->pair_kernel_pref != 1 && mmm_pair_n3_eligible(h)) return 2;
+  return 1;
+}
+
+static void free_scratch(mmm_system* h) {
+  cudaStreamSynchronize(h->stream);
+  if (h->d_fpair) { cudaFree(h->d_fpair); h->d_fpair = nullptr; }
+  if (h->d_epair) { cudaFree(h->d_epair); h->d_epair = nullptr; }
+  if (h->d_facc) { cudaFree(h->d_facc); h->d_facc = nullptr; }
+  if (h->d_items) { cudaFree(h->d_items); h->d_items = nullptr; }
+  h->scratch_sig = -1;
+}
+
+// Size the pair-kernel work decomposition and its scratch for the kernel that will run.
 static int ensure_scratch(mmm_system* h) {
-  if (h->d_fpair) return MMM_OK;
-  const int64_t niblk = h->npad / MMM_IBLOCK;
-  const int64_t stages = h->ntiles / (MMM_STAGE / MMM_TILE);
-  int64_t nchunk = 1;
-  if (any_pair_term(h)) {
-    const int64_t target = (int64_t)h->sm_count * 4 * 6;  // ~6 items per resident CTA
-    nchunk = (target + niblk - 1) / niblk;
-    nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, std::min<int64_t>(stages, 64)));
-    // chunks are whole stages; recompute the count so that no chunk is empty
-    const int64_t chunk_stages = (stages + nchunk - 1) / nchunk;
-    nchunk = (stages + chunk_stages - 1) / chunk_stages;
-  }
-  h->nchunk = (int)nchunk;
-  h->chunk_tiles = (int)((stages + nchunk - 1) / nchunk) * (MMM_STAGE / MMM_TILE);
-  h->n_items = niblk * nchunk;
+  const int mode = wanted_pair_mode(h);
+  if (h->scratch_sig == mode) return MMM_OK;
+  free_scratch(h);
+  h->pair_mode = mode;
   int rc;
-  if ((rc = dev_alloc(h, &h->d_fpair, (size_t)nchunk * 3 * (size_t)h->npad))) return rc;
+  if (mode == 2) {
+    // Newton-3: fixed-point force planes + work-item table
+    std::vector<int2> items;
+    mmm_n3_build_items(h, items, &h->n3_cj);
+    h->n_items = (int64_t)items.size();
+    h->nchunk = 1;
+    if ((rc = dev_alloc(h, &h->d_items, items.size()))) return rc;
+    MMM_CUDA(h, cudaMemcpyAsync(h->d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
+  } else if (mode == 3) {
+    h->n_items = mmm_cells_energy_slots(h);
+    h->nchunk = 1;
+    if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
+  } else {
+    // gather kernel: items = i-blocks x j-chunks, enough of them that the dynamic scheduler keeps
+    // every SM busy to the end; one partial-force plane per chunk
+    const int64_t niblk = h->npad / MMM_IBLOCK;
+    const int64_t stages = h->ntiles / (MMM_STAGE / MMM_TILE);
+    int64_t nchunk = 1;
+    if (mode == 1) {
+      const int64_t target = (int64_t)h->sm_count * 4 * 6;  // ~6 items per resident CTA
+      nchunk = (target + niblk - 1) / niblk;
+      nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, std::min<int64_t>(stages, 64)));
+      // chunks are whole stages; recompute the count so that no chunk is empty
+      const int64_t chunk_stages = (stages + nchunk - 1) / nchunk;
+      nchunk = (stages + chunk_stages - 1) / chunk_stages;
+    }
+    h->nchunk = (int)nchunk;
+    h->chunk_tiles = (int)((stages + nchunk - 1) / nchunk) * (MMM_STAGE / MMM_TILE);
+    h->n_items = niblk * nchunk;
+    if (mode == 1) {
+      if ((rc = dev_alloc(h, &h->d_fpair, (size_t)nchunk * 3 * (size_t)h->npad))) return rc;
+      MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * (size_t)nchunk * 3 * (size_t)h->npad, h->stream));
+    }
+  }
   if ((rc = dev_alloc(h, &h->d_epair, (size_t)h->n_items * 4))) return rc;
-  MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * (size_t)nchunk * 3 * (size_t)h->npad, h->stream));
   MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
+  h->scratch_sig = mode;
   return MMM_OK;
 }
 
@@ -417,28 +461,16 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
   if (h->topo_dirty && (rc = mmm_upload_topology(h))) return rc;
   if ((rc = ensure_scratch(h))) return rc;
   if ((rc = mmm_launch_prepare(h, d_skip))) return rc;
-  if (any_pair_term(h)) {
-    if (h->cutoff > 0.0) rc = mmm_launch_pair_cutoff(h, d_skip);
-    else rc = mmm_launch_pair_exact(h, d_skip);
-    if (rc) return rc;
-  }
+  if (h->pair_mode == 3) rc = mmm_launch_pair_cutoff(h, d_skip);
+  else if (h->pair_mode == 2) rc = mmm_launch_pair_n3(h, d_skip);
+  else if (h->pair_mode == 1) rc = mmm_launch_pair_exact(h, d_skip);
+  if (rc) return rc;
   return mmm_launch_assemble(h, d_skip);
 }
 
 static int check_ready(mmm_system* h) {
   if (!h->positions_set) return mmm_fail(h, MMM_ERR_STATE, "positions were never set");
   return MMM_OK;
-}
-
-// changing whether any pair term exists changes the work decomposition
-static void invalidate_scratch_if_needed(mmm_system* h) {
-  const int sig = any_pair_term(h) ? 1 : 0;
-  if (h->d_fpair && h->scratch_sig != sig) {
-    cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_fpair); h->d_fpair = nullptr;
-    cudaFree(h->d_epair); h->d_epair = nullptr;
-  }
-  h->scratch_sig = sig;
 }
 
 extern "C" {
@@ -448,7 +480,6 @@ int mmm_energy_forces_device(mmm_handle h, double* e_terms, double* d_forces) {
   int rc = check_ready(h);
   if (rc) return rc;
   cudaSetDevice(h->device);
-  invalidate_scratch_if_needed(h);
   if ((rc = mmm_evaluate(h, nullptr))) return rc;
   if ((rc = mmm_launch_finalize_energy(h))) return rc;
   double e[MMM_NUM_TERMS];
@@ -456,7 +487,7 @@ int mmm_energy_forces_device(mmm_handle h, double* e_terms, double* d_forces) {
   if (d_forces)
     MMM_CUDA(h, cudaMemcpyAsync(d_forces, h->d_g, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToDevice, h->stream));
   MMM_CUDA(h, cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&h->last_pair_ms, h->ev_a, h->ev_b);
+  if (h->pair_mode != 0) cudaEventElapsedTime(&h->last_pair_ms, h->ev_a, h->ev_b);
   double tot = 0;
   for (int t = 0; t < MMM_NUM_TERMS; ++t) tot += e[t];
   if (e_terms) memcpy(e_terms, e, sizeof(e));
@@ -481,13 +512,12 @@ int mmm_evaluate_n(mmm_handle h, int n) {
   int rc = check_ready(h);
   if (rc) return rc;
   cudaSetDevice(h->device);
-  invalidate_scratch_if_needed(h);
   for (int q = 0; q < n; ++q) {
     if ((rc = mmm_evaluate(h, nullptr))) return rc;
     if ((rc = mmm_launch_finalize_energy(h))) return rc;
   }
   MMM_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (any_pair_term(h)) cudaEventElapsedTime(&h->last_pair_ms, h->ev_a, h->ev_b);
+  if (h->pair_mode != 0) cudaEventElapsedTime(&h->last_pair_ms, h->ev_a, h->ev_b);
   return MMM_OK;
 }
 
@@ -497,7 +527,6 @@ int mmm_evaluate_timed(mmm_handle h, int n, int flush_l2, float* total_ms, float
   int rc = check_ready(h);
   if (rc) return rc;
   cudaSetDevice(h->device);
-  invalidate_scratch_if_needed(h);
   const size_t flush_bytes = (size_t)256 << 20;
   if (flush_l2 && !h->d_flush) MMM_CUDA(h, cudaMalloc(&h->d_flush, flush_bytes));
   while (h->ev_pool.size() < (size_t)2 * n + 2) {
@@ -539,7 +568,6 @@ int mmm_minimize(mmm_handle h, double tol, int64_t max_iter, mmm_min_report* out
   int rc = check_ready(h);
   if (rc) return rc;
   cudaSetDevice(h->device);
-  invalidate_scratch_if_needed(h);
   const size_t n3 = 3 * (size_t)h->n;
   if (!h->d_xp) {
     if ((rc = dev_alloc(h, &h->d_xp, n3))) return rc;
@@ -552,6 +580,15 @@ int mmm_minimize(mmm_handle h, double tol, int64_t max_iter, mmm_min_report* out
 }
 
 int64_t mmm_launch_count(mmm_handle h) { return h ? h->launches : 0; }
+
+int mmm_set_pair_kernel(mmm_handle h, int which) {
+  if (!h) return MMM_ERR_ARG;
+  REQUIRE(h, which == 0 || which == 1, "mmm_set_pair_kernel: 0 = automatic, 1 = gather kernel");
+  h->pair_kernel_pref = which;
+  return MMM_OK;
+}
+
+int mmm_pair_kernel_in_use(mmm_handle h) { return h ? h->pair_mode : 0; }
 
 int mmm_last_pair_kernel_ms(mmm_handle h, float* ms_out) {
   if (!h || !ms_out) return MMM_ERR_ARG;

@@ -20,7 +20,8 @@ constexpr int kAsmBlock = MMM_ASM_BLOCK;
 
 struct AsmArgs {
   const double* x;
-  const double* fpair;
+  const double* fpair;       // gather kernel: [nchunk][3][npad] partial forces
+  unsigned long long* facc;  // Newton-3 kernel: [3][npad] fixed-point force (2^-24), zeroed here after use
   int nchunk;
   int64_t n, npad;
   const int* bl_ptr; const int* bl_partner; const int* bl_flags; const double* bl_r0; const double* bl_k;
@@ -62,11 +63,21 @@ __global__ void __launch_bounds__(kAsmBlock) k_assemble(const AsmArgs A) {
   double e_sc = 0, e_lam = 0, e_cf = 0, e_bond = 0, e_loop = 0, e_ang = 0;
   if (i < A.n) {
     double fx = 0, fy = 0, fz = 0;
-    for (int c = 0; c < A.nchunk; ++c) {
-      const double* fp = A.fpair + (size_t)c * 3 * (size_t)A.npad;
-      fx += fp[i];
-      fy += fp[(size_t)A.npad + i];
-      fz += fp[2 * (size_t)A.npad + i];
+    if (A.facc) {
+      const double inv = 1.0 / 16777216.0;
+      fx = (double)(long long)A.facc[i] * inv;
+      fy = (double)(long long)A.facc[(size_t)A.npad + i] * inv;
+      fz = (double)(long long)A.facc[2 * (size_t)A.npad + i] * inv;
+      A.facc[i] = 0ull;
+      A.facc[(size_t)A.npad + i] = 0ull;
+      A.facc[2 * (size_t)A.npad + i] = 0ull;
+    } else if (A.fpair) {
+      for (int c = 0; c < A.nchunk; ++c) {
+        const double* fp = A.fpair + (size_t)c * 3 * (size_t)A.npad;
+        fx += fp[i];
+        fy += fp[(size_t)A.npad + i];
+        fz += fp[2 * (size_t)A.npad + i];
+      }
     }
     const double xi = A.x[3 * i], yi = A.x[3 * i + 1], zi = A.x[3 * i + 2];
 
@@ -311,7 +322,8 @@ int mmm_upload_angles(mmm_system* h, const int32_t* ai, const int32_t* aj, const
 int mmm_launch_assemble(mmm_system* h, const int* d_skip) {
   AsmArgs A;
   A.x = h->d_x;
-  A.fpair = h->d_fpair;
+  A.fpair = h->pair_mode == 1 ? h->d_fpair : nullptr;
+  A.facc = h->pair_mode == 2 ? h->d_facc : nullptr;
   A.nchunk = h->nchunk;
   A.n = h->n;
   A.npad = h->npad;

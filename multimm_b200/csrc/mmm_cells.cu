@@ -6,6 +6,8 @@
 // MMM_ERR_STATE instead of silently falling back to anything.
 #include "mmm_internal.cuh"
 
+int64_t mmm_cells_energy_slots(const mmm_system* h) { (void)h; return 1; }
+
 int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
   (void)d_skip;
   return mmm_fail(h, MMM_ERR_STATE, "cutoff mode is not available in this build; use mmm_set_cutoff(h, 0)");

@@ -19,8 +19,14 @@ constexpr int MMM_STAGE = 256;        // j-beads staged in shared memory at a ti
 constexpr int MMM_ASM_BLOCK = 128;    // threads per block of the O(N) assemble kernel
 constexpr int MMM_LBFGS_M = 6;        // history length (liblbfgs default used by OpenMM)
 constexpr int MMM_NDOT = 6 * MMM_LBFGS_M + 7;  // dot products per evaluation (vector-free L-BFGS)
-constexpr float MMM_PAD_COORD = 1.0e10f;       // padded beads sit here: every pair term underflows to 0
-constexpr int MMM_PAD_CHROM = 0xFFFF;
+constexpr int MMM_PAD_TO = 512;       // npad is a multiple of this (i-block of the Newton-3 pair kernel)
+// Padding bead k (k = i - n < MMM_PAD_TO) sits at x = y = z = MMM_PAD_COORD + k * MMM_PAD_STEP, so
+// far away that every pair term with a real bead underflows to 0, and pads are also far from each
+// other (no r = 0 pair).  It carries the chromosome id MMM_PAD_CHROM + k: equal to no real id and
+// to no other pad, so chromosome-block work never sees a pad pair as "same chromosome".
+constexpr float MMM_PAD_COORD = 1.0e10f;
+constexpr float MMM_PAD_STEP = 1.0e7f;
+constexpr int MMM_PAD_CHROM = 0xFC00;  // real chromosome ids are < this
 
 // bead type bits carried in pos4.w (bit pattern of an int):
 //   [2:0]  s + 2                (sub-compartment label, model.py Cs in {-2..2})
@@ -91,7 +97,7 @@ enum ApplyFlag { APPLY_NONE = 0, APPLY_INIT = 1, APPLY_RETRY = 2, APPLY_ACCEPT =
 struct mmm_system {
   int device = 0;
   int64_t n = 0;       // beads
-  int64_t npad = 0;    // padded to a multiple of MMM_IBLOCK
+  int64_t npad = 0;    // padded to a multiple of MMM_PAD_TO
   int64_t ntiles = 0;  // npad / MMM_TILE
   cudaStream_t stream = nullptr;
   int sm_count = 148;
@@ -140,6 +146,13 @@ struct mmm_system {
   double* d_epair = nullptr;     // [items][4]
   int64_t n_items = 0;
   int* d_counter = nullptr;      // dynamic work counter
+  // pair_mode: which kernel the scratch is sized for. 0 none, 1 gather (mmm_pair.cu),
+  // 2 Newton-3 (mmm_pair_n3.cu), 3 cut-off cell list (mmm_cells.cu)
+  int pair_mode = 0;
+  int pair_kernel_pref = 0;      // 0 auto, 1 force the gather kernel (tests / A-B timing)
+  unsigned long long* d_facc = nullptr;  // [3][npad] fixed-point force accumulator (Newton-3, cells)
+  int2* d_items = nullptr;       // Newton-3 work items
+  int n3_cj = 1;                 // j-stages per item
 
   // reductions
   int n_red_blocks = 0;
@@ -195,8 +208,13 @@ int mmm_launch_hilbert(mmm_system* h, int p, double spacing, int32_t* d_ijk);
 // mmm_pair.cu
 int mmm_launch_pair_exact(mmm_system* h, const int* d_skip);  // d_pos4 -> d_fpair, d_epair
 bool mmm_pair_fast_path(const mmm_system* h);
+// mmm_pair_n3.cu
+bool mmm_pair_n3_eligible(const mmm_system* h);
+int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, int* cj_out);
+int mmm_launch_pair_n3(mmm_system* h, const int* d_skip);  // d_pos4 -> d_facc, d_epair
 // mmm_cells.cu
 int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip);
+int64_t mmm_cells_energy_slots(const mmm_system* h);
 // mmm_bonded.cu
 int mmm_upload_topology(mmm_system* h);
 int mmm_upload_angles(mmm_system* h, const int32_t* ai, const int32_t* aj, const int32_t* ak,

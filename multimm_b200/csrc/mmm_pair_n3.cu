@@ -1,0 +1,550 @@
+// mmm_pair_n3.cu — exact all-pairs ("NoCutoff") pair kernel, Newton's-third-law formulation,
+// for sm_100a.  Default path for the reference's default functional forms: power-law EV with an
+// integer power (model.py:199), Gaussian COB/SCB (model.py:246-250, 322-328), polynomial CHB
+// (model.py:416-419).  Every unordered pair is evaluated ONCE (the gather kernel in mmm_pair.cu
+// visits it from both sides), and the result is still bit-reproducible.
+//
+// Decomposition
+//   i-block  = 512 consecutive beads, stationary in registers for a whole work item:
+//              warp w owns 64 of them, lane (a = lane >> 2, b = lane & 3) holds the 8 beads
+//              64 w + 8 a + {0..7}; the four b-lanes of a group hold the same beads.
+//   j-stage  = 256 consecutive beads in shared memory (float4 xyz + type bits), double buffered.
+//   step     = one tile of 32 j-beads: register ii of lane (a, b) meets j-bead 4 (jj ^ a) + b,
+//              jj = 0..7, so a lane evaluates an 8 x 8 rectangle = 64 pairs and a warp 64 x 32.
+//   item     = (i-block, run of <= cj j-stages), handed out by an atomic counter; only j-stages at
+//              or above the diagonal exist.  The two stages that overlap the i-block itself are
+//              evaluated in "diagonal" mode: ordered pairs, i-side only, energy halved, self masked.
+//
+// Accumulation (all in units of U = p eps sigma^p, the EV force prefactor)
+//   i side : 24 FP32 registers per lane for the whole item, butterfly over the 4 b-lanes at the
+//            end, then 64-bit fixed-point RED.ADD to facc[3][npad].
+//   j side : 24 FP32 registers per step.  The XOR mapping above makes the reduce-scatter over
+//            the 8 a-lanes select-free: 12 + 6 + 3 SHFL.BFLY/FADD pairs leave lane l holding the
+//            total for j-bead 32 step + l, which it adds to its warp's private shared-memory
+//            column.  After the stage, thread t sums the 8 warp columns of j-bead t in fixed
+//            order and issues 3 fixed-point REDs.
+//   Integer addition is associative, so the force is independent of which CTA ran which item
+//   and in which order: deterministic per-bead accumulation without a partial-sum buffer per
+//   chunk.  Resolution 2^-24 kJ/mol/nm, range +-5.5e11.
+//   energies: FP32 within a stage, FP64 across stages, one slot per item (fixed order).
+//
+// Tile classification is warp-uniform, from the 32-bead bounding boxes / chromosome ranges of
+// k_prepare: far tiles skip the Gaussians (< 2^-40 of their prefactor), CHB only where the
+// chromosome ranges overlap, per-pair chromosome compare only when a tile is not
+// single-chromosome.  The hot variant (far, no CHB) is 21 FP32-pipe/MUFU instructions per
+// unordered pair: 3 FADD, FMUL + 2 FFMA (r^2), MUFU.SQRT, FFMA (q = r^2 + r_s r), MUFU.RCP
+// (w/r), FMUL (w), 3 FMUL (w^6), FADD (energy), FMUL, 6 FFMA (both force accumulators).
+// Roofline: instruction issue (128 lanes/clk/SM); MUFU.SQRT/RCP co-issue (measured 32 lanes/clk/SM).
+#include "mmm_internal.cuh"
+
+namespace {
+
+constexpr int N3_THREADS = 256;
+constexpr int N3_WARPS = N3_THREADS / 32;
+constexpr int N3_IB = 512;                 // i-beads per block
+constexpr int N3_JB = 256;                 // j-beads per stage
+constexpr int N3_STEPS = N3_JB / MMM_TILE; // 8
+constexpr double N3_FIXED = 16777216.0;    // 2^24
+
+static_assert(N3_IB == MMM_PAD_TO, "npad must be a multiple of the i-block");
+static_assert(N3_IB == N3_WARPS * 64, "a warp owns 64 i-beads");
+
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int P>
+__device__ __forceinline__ float powi(float w) {
+  if constexpr (P == 1) {
+    return w;
+  } else if constexpr (P % 2 == 0) {
+    const float hf = powi<P / 2>(w);
+    return hf * hf;
+  } else {
+    return w * powi<P - 1>(w);
+  }
+}
+
+struct N3Consts {
+  float ev_rs;
+  float g_c;       // -log2(e) / (2 rc^2)
+  float rg2;       // Gaussian range^2 (box test)
+  float chb_kc;
+  float chb_c;     // dE / U
+  float a_scb[5];  // eps(s) / (rc^2 U), indexed by s + 2
+  float a_cob[4];  // by class bits: [1] = A, [2] = B, others 0
+  int gk;          // bit 0: SCB on, bit 1: COB on
+};
+
+struct N3Args {
+  const float4* pos4;
+  const TileInfo* tiles;
+  unsigned long long* facc;  // [3][npad] fixed-point force, units 2^-24 kJ/mol/nm
+  double* epair;             // [n_items][4]
+  const int2* items;         // (i-block, first j-stage)
+  int* counter;
+  const int* skip;
+  int64_t npad;
+  int n_items, n_jstages, cj;
+  double fscale;             // U * 2^24
+  double e_ev, e_gauss, e_chb;  // energy prefactors: eps sigma^p; -rc^2 U; dE
+  N3Consts c;
+};
+
+struct IBeads {
+  float x[8], y[8], z[8];
+  float fx[8], fy[8], fz[8];
+};
+
+struct EAcc {
+  float ev, scb, cob, chb;
+};
+
+// Two j-beads (registers jj0, jj0 + 1 of the XOR mapping) against this lane's 8 i-beads: 16 pairs.
+// GAUSS: evaluate the Gaussian block terms (runtime c.gk says which); CHBM: 0 none, 1 every pair
+// is same-chromosome, 2 compare per pair; SELF: mask i == j (diagonal stages).
+// si4: this lane's i-beads in shared memory (type bits for the slow variants).
+template <int EVP, int GK, int CHBM, bool SELF>
+__device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int a, const int b, const int jj0,
+                                        IBeads& I, float (&cx)[2], float (&cy)[2], float (&cz)[2],
+                                        EAcc& E, const N3Consts& c, const float4* __restrict__ si4,
+                                        const int self_d) {
+  constexpr bool GAUSS = GK != 0;
+  constexpr bool kTypes = GAUSS || CHBM == 2;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int jl = (((jj0 + k) ^ a) << 2) | b;
+    const float4 pj = sj[jl];
+    const int tj = __float_as_int(pj.w);
+    // a Gaussian term is non-zero only for equal labels / classes, so its prefactor can be looked
+    // up from the j-bead once per 8 pairs
+    float aj_scb = 0.0f, aj_cob = 0.0f;
+    if (GK & 1) aj_scb = c.a_scb[tj & 7];
+    if (GK & 2) aj_cob = c.a_cob[(tj >> 3) & 3];
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const float dx = I.x[ii] - pj.x, dy = I.y[ii] - pj.y, dz = I.z[ii] - pj.z;
+      float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      bool self = false;
+      if (SELF) {
+        self = (jl - ii) == self_d;
+        r2 = self ? 1.0f : r2;
+      }
+      const float r = fast_sqrt(r2);
+      const float q = fmaf(c.ev_rs, r, r2);
+      const float wr = fast_rcp(q);  // w / r with w = 1 / (r + r_s)
+      const float w = r * wr;
+      float wp = powi<EVP>(w);
+      if (SELF) wp = self ? 0.0f : wp;
+      E.ev += wp;
+      float fs = wp * wr;  // -(dE_ev/dr) / r in units of U
+      if (kTypes) {
+        const int ti = __float_as_int(si4[ii].w);
+        const int xr = ti ^ tj;
+        if (GAUSS) {
+          float g = fast_ex2(r2 * c.g_c);
+          if (SELF) g = self ? 0.0f : g;
+          if (GK & 1) {
+            const float t = ((xr & 0x7) == 0) ? aj_scb * g : 0.0f;
+            E.scb += t;
+            fs -= t;
+          }
+          if (GK & 2) {
+            const float t = ((xr & 0x18) == 0) ? aj_cob * g : 0.0f;
+            E.cob += t;
+            fs -= t;
+          }
+        }
+        if (CHBM == 2) {
+          // E = dE (kC r^4 - r^3 + r^2);  -(dE/dr)/r = -dE (4 kC r^2 - 3 r + 2)
+          bool same = (xr & 0xFFFF00) == 0;
+          if (SELF) same = same && !self;
+          const float e = r2 * fmaf(c.chb_kc, r2, 1.0f - r);
+          const float bb = fmaf(-3.0f, r, fmaf(4.0f * c.chb_kc, r2, 2.0f));
+          E.chb += same ? e : 0.0f;
+          fs = fmaf(-c.chb_c, same ? bb : 0.0f, fs);
+        }
+      }
+      if (CHBM == 1) {
+        E.chb = fmaf(r2, fmaf(c.chb_kc, r2, 1.0f - r), E.chb);
+        fs = fmaf(-c.chb_c, fmaf(-3.0f, r, fmaf(4.0f * c.chb_kc, r2, 2.0f)), fs);
+      }
+      I.fx[ii] = fmaf(fs, dx, I.fx[ii]);
+      I.fy[ii] = fmaf(fs, dy, I.fy[ii]);
+      I.fz[ii] = fmaf(fs, dz, I.fz[ii]);
+      ax = fmaf(fs, dx, ax);
+      ay = fmaf(fs, dy, ay);
+      az = fmaf(fs, dz, az);
+    }
+    cx[k] = ax; cy[k] = ay; cz[k] = az;
+  }
+}
+
+#define N3_SHFL3(dst, src, m)                                  \
+  dst##x = __shfl_xor_sync(0xffffffffu, src##x, m);            \
+  dst##y = __shfl_xor_sync(0xffffffffu, src##y, m);            \
+  dst##z = __shfl_xor_sync(0xffffffffu, src##z, m);
+
+// One step: this lane's 8 i-beads against its 8 j-beads of the tile at sj[0..31], as a ROLLED loop
+// over four groups of two j-registers (the body is 16 pairs, ~5 KB of SASS, so that it stays in the
+// instruction cache), with the reduce-scatter over the 8 a-lanes folded in between the groups.
+// Register jj of lane (a, b) holds j-bead 4 (jj ^ a) + b, so lanes L and L ^ 8 (a bit 1) hold the
+// same beads in registers r and r ^ 2, L and L ^ 16 in r and r ^ 4, L and L ^ 4 in r and r ^ 1:
+// partners exchange matching beads without selects.  12 + 6 + 3 SHFL.BFLY/FADD pairs leave lane l
+// with the warp's total for j-bead l of the tile (returned in out[3]).  WANT_J false (diagonal
+// stages, ordered pairs): the j side is dropped.
+template <int EVP, int GK, int CHBM, bool SELF, bool WANT_J>
+__device__ __forceinline__ void step64(const float4* __restrict__ sj, const int a, const int b, IBeads& I,
+                                       float (&out)[3], EAcc& E, const N3Consts& c,
+                                       const float4* __restrict__ si4, const int self_d) {
+  float s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;  // saved group (g even)
+  float p0x = 0.f, p0y = 0.f, p0z = 0.f, p1x = 0.f, p1y = 0.f, p1z = 0.f;  // registers 0,1 after level "2"
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    float cx[2], cy[2], cz[2];
+    pairs16<EVP, GK, CHBM, SELF>(sj, a, b, 2 * g, I, cx, cy, cz, E, c, si4, self_d);
+    if (!WANT_J) continue;
+    if ((g & 1) == 0) {
+      s0x = cx[0]; s0y = cy[0]; s0z = cz[0];
+      s1x = cx[1]; s1y = cy[1]; s1z = cz[1];
+    } else {
+      float t0x, t0y, t0z, t1x, t1y, t1z;
+      const float c0x = cx[0], c0y = cy[0], c0z = cz[0], c1x = cx[1], c1y = cy[1], c1z = cz[1];
+      N3_SHFL3(t0, c0, 8)
+      N3_SHFL3(t1, c1, 8)
+      t0x += s0x; t0y += s0y; t0z += s0z;
+      t1x += s1x; t1y += s1y; t1z += s1z;
+      if (g == 1) {
+        p0x = t0x; p0y = t0y; p0z = t0z;
+        p1x = t1x; p1y = t1y; p1z = t1z;
+      } else {
+        float u0x, u0y, u0z, u1x, u1y, u1z;
+        N3_SHFL3(u0, t0, 16)
+        N3_SHFL3(u1, t1, 16)
+        p0x += u0x; p0y += u0y; p0z += u0z;
+        p1x += u1x; p1y += u1y; p1z += u1z;
+      }
+    }
+  }
+  if (WANT_J) {
+    float vx, vy, vz;
+    N3_SHFL3(v, p1, 4)
+    out[0] = p0x + vx; out[1] = p0y + vy; out[2] = p0z + vz;
+  }
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void red_fixed(unsigned long long* p, float v, double fscale, double& poison) {
+  if (!(fabsf(v) <= 3.0e38f)) poison = __longlong_as_double(0x7ff8000000000000LL);  // NaN/Inf force
+  const long long q = __double2ll_rn((double)v * fscale);
+  atomicAdd(p, (unsigned long long)q);
+}
+
+template <int EVP, int GK, bool CHB>
+__global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
+  __shared__ __align__(16) float4 s_j[2][N3_JB];
+  __shared__ __align__(16) TileInfo s_jt[2][N3_STEPS];
+  __shared__ __align__(16) float4 s_i[N3_IB];
+  __shared__ float s_acc[N3_WARPS][3][N3_JB];
+  __shared__ double s_red[4][N3_WARPS];
+  __shared__ int s_item;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a = lane >> 2, b = lane & 3;
+  const N3Consts& c = A.c;
+  if (A.skip && *A.skip) return;
+
+#pragma unroll
+  for (int w = 0; w < N3_WARPS; ++w)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) s_acc[w][d][tid] = 0.0f;
+
+  for (;;) {
+    __syncthreads();  // protects s_item, s_i, s_j, s_red across items
+    if (tid == 0) s_item = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= A.n_items) break;
+    const int2 it = A.items[item];
+    const int iblk = it.x, js0 = it.y, js1 = min(js0 + A.cj, A.n_jstages);
+    const int64_t ibase = (int64_t)iblk * N3_IB;
+    const int iw = warp * 64 + a * 8;  // first of this lane's i-beads within the block
+
+    // the i-block: registers (positions) and shared memory (type bits for the slow variants)
+    IBeads I;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const float4 p = A.pos4[ibase + iw + ii];
+      I.x[ii] = p.x; I.y[ii] = p.y; I.z[ii] = p.z;
+      I.fx[ii] = 0.0f; I.fy[ii] = 0.0f; I.fz[ii] = 0.0f;
+      if ((ii >> 1) == b) s_i[iw + ii] = p;
+    }
+    // bounding box / chromosome range of the warp's 64 i-beads (two tiles); a padding-only tile
+    // does not widen the box
+    TileInfo ib = A.tiles[(ibase >> 5) + warp * 2];
+    {
+      const TileInfo ib2 = A.tiles[(ibase >> 5) + warp * 2 + 1];
+      if (ib.cmin >= MMM_PAD_CHROM) {
+        ib = ib2;
+      } else if (ib2.cmin < MMM_PAD_CHROM) {
+        ib.lox = fminf(ib.lox, ib2.lox); ib.loy = fminf(ib.loy, ib2.loy); ib.loz = fminf(ib.loz, ib2.loz);
+        ib.hix = fmaxf(ib.hix, ib2.hix); ib.hiy = fmaxf(ib.hiy, ib2.hiy); ib.hiz = fmaxf(ib.hiz, ib2.hiz);
+        ib.cmin = min(ib.cmin, ib2.cmin); ib.cmax = max(ib.cmax, ib2.cmax);
+      }
+    }
+    const bool i_all_pad = ib.cmin >= MMM_PAD_CHROM;
+
+    // first stage
+    s_j[0][tid] = A.pos4[(int64_t)js0 * N3_JB + tid];
+    if (tid < 2 * N3_STEPS)
+      reinterpret_cast<float4*>(s_jt[0])[tid] = reinterpret_cast<const float4*>(A.tiles + (int64_t)js0 * N3_STEPS)[tid];
+    __syncthreads();
+
+    double de0 = 0.0, de1 = 0.0, de2 = 0.0, de3 = 0.0, poison = 0.0;
+
+    for (int js = js0; js < js1; ++js) {
+      const int buf = (js - js0) & 1;
+      const bool more = js + 1 < js1;
+      float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f), nxt_t = nxt;
+      if (more) {
+        nxt = A.pos4[(int64_t)(js + 1) * N3_JB + tid];
+        if (tid < 2 * N3_STEPS)
+          nxt_t = reinterpret_cast<const float4*>(A.tiles + (int64_t)(js + 1) * N3_STEPS)[tid];
+      }
+      const bool diag = (js >> 1) == iblk;
+      // global j index minus global i index of (jl = 0, ii = 0): self pair when jl - ii == -that
+      const int self_base = (int)(ibase + iw - (int64_t)js * N3_JB);
+      EAcc E;
+      E.ev = E.scb = E.cob = E.chb = 0.0f;
+
+      if (!i_all_pad) {
+        for (int step = 0; step < N3_STEPS; ++step) {
+          const TileInfo jt = s_jt[buf][step];
+          if (jt.cmin >= MMM_PAD_CHROM) continue;  // padding only
+          const float4* sj = s_j[buf] + step * MMM_TILE;
+          float fj[3];
+          if (diag) {
+            const int self_d = self_base - step * MMM_TILE;
+            step64<EVP, GK, CHB ? 2 : 0, true, false>(sj, a, b, I, fj, E, c, s_i + iw, self_d);
+            continue;  // ordered pairs: the j side is somebody's i side in this same stage pair
+          }
+          int chb_mode = 0;
+          if (CHB) {
+            const bool overlap = !(ib.cmax < jt.cmin || jt.cmax < ib.cmin);
+            const bool uniform = (ib.cmin == ib.cmax) && (jt.cmin == jt.cmax);
+            chb_mode = overlap ? (uniform ? 1 : 2) : 0;
+          }
+          bool near = false;
+          if (GK != 0) {
+            const float ddx = fmaxf(0.0f, fmaxf(ib.lox - jt.hix, jt.lox - ib.hix));
+            const float ddy = fmaxf(0.0f, fmaxf(ib.loy - jt.hiy, jt.loy - ib.hiy));
+            const float ddz = fmaxf(0.0f, fmaxf(ib.loz - jt.hiz, jt.loz - ib.hiz));
+            near = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) < c.rg2;
+          }
+          if (near) {
+            step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+          } else if (!CHB || chb_mode == 0) {
+            step64<EVP, 0, 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+          } else if (chb_mode == 1) {
+            step64<EVP, 0, CHB ? 1 : 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+          } else {
+            step64<EVP, 0, CHB ? 2 : 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+          }
+          // lane (a, b) now holds j-bead 4 a + b = lane of this step; force on j is -sum
+          const int col = step * MMM_TILE + lane;
+          s_acc[warp][0][col] -= fj[0];
+          s_acc[warp][1][col] -= fj[1];
+          s_acc[warp][2][col] -= fj[2];
+        }
+      }
+      const double wgt = diag ? 0.5 : 1.0;
+      de0 += wgt * (double)E.ev;
+      de1 += wgt * (double)E.cob;
+      de2 += wgt * (double)E.scb;
+      de3 += wgt * (double)E.chb;
+
+      if (more) {
+        s_j[buf ^ 1][tid] = nxt;
+        if (tid < 2 * N3_STEPS) reinterpret_cast<float4*>(s_jt[buf ^ 1])[tid] = nxt_t;
+      }
+      __syncthreads();
+      if (!diag) {
+        // j-side emission: thread t owns j-bead t of the stage
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+#pragma unroll
+        for (int w = 0; w < N3_WARPS; ++w) {
+          sx += s_acc[w][0][tid]; sy += s_acc[w][1][tid]; sz += s_acc[w][2][tid];
+          s_acc[w][0][tid] = 0.0f; s_acc[w][1][tid] = 0.0f; s_acc[w][2][tid] = 0.0f;
+        }
+        const int64_t j = (int64_t)js * N3_JB + tid;
+        if (sx != 0.0f || sy != 0.0f || sz != 0.0f) {
+          red_fixed(A.facc + j, sx, A.fscale, poison);
+          red_fixed(A.facc + A.npad + j, sy, A.fscale, poison);
+          red_fixed(A.facc + 2 * A.npad + j, sz, A.fscale, poison);
+        }
+      }
+      __syncthreads();
+    }
+
+    // i-side emission: butterfly over the 4 b-lanes, then lane b emits beads 2b and 2b + 1
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      I.fx[ii] += __shfl_xor_sync(0xffffffffu, I.fx[ii], 1);
+      I.fy[ii] += __shfl_xor_sync(0xffffffffu, I.fy[ii], 1);
+      I.fz[ii] += __shfl_xor_sync(0xffffffffu, I.fz[ii], 1);
+      I.fx[ii] += __shfl_xor_sync(0xffffffffu, I.fx[ii], 2);
+      I.fy[ii] += __shfl_xor_sync(0xffffffffu, I.fy[ii], 2);
+      I.fz[ii] += __shfl_xor_sync(0xffffffffu, I.fz[ii], 2);
+    }
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      if ((ii >> 1) == b) {
+        const int64_t i = ibase + iw + ii;
+        red_fixed(A.facc + i, I.fx[ii], A.fscale, poison);
+        red_fixed(A.facc + A.npad + i, I.fy[ii], A.fscale, poison);
+        red_fixed(A.facc + 2 * A.npad + i, I.fz[ii], A.fscale, poison);
+      }
+    }
+
+    // energies of the item, fixed order
+    de0 = de0 * A.e_ev + poison;
+    de1 *= A.e_gauss;
+    de2 *= A.e_gauss;
+    de3 *= A.e_chb;
+    de0 = warp_sum_d(de0); de1 = warp_sum_d(de1); de2 = warp_sum_d(de2); de3 = warp_sum_d(de3);
+    if (lane == 0) { s_red[0][warp] = de0; s_red[1][warp] = de1; s_red[2][warp] = de2; s_red[3][warp] = de3; }
+    __syncthreads();
+    if (tid < 4) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < N3_WARPS; ++w) s += s_red[tid][w];
+      A.epair[(size_t)item * 4 + tid] = s;
+    }
+  }
+}
+
+template <int EVP, int GK, bool CHB>
+int launch_n3(mmm_system* h, const N3Args& A) {
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pair_n3<EVP, GK, CHB>, N3_THREADS, 0);
+  if (occ < 1) occ = 1;
+  int grid = h->sm_count * occ;
+  if (grid > A.n_items) grid = A.n_items;
+  k_pair_n3<EVP, GK, CHB><<<grid, N3_THREADS, 0, h->stream>>>(A);
+  return 0;
+}
+
+template <int EVP>
+int launch_n3_evp(mmm_system* h, const N3Args& A, int gk, bool chb) {
+  switch (gk * 2 + (chb ? 1 : 0)) {
+    case 0: return launch_n3<EVP, 0, false>(h, A);
+    case 1: return launch_n3<EVP, 0, true>(h, A);
+    case 2: return launch_n3<EVP, 1, false>(h, A);
+    case 3: return launch_n3<EVP, 1, true>(h, A);
+    case 4: return launch_n3<EVP, 2, false>(h, A);
+    case 5: return launch_n3<EVP, 2, true>(h, A);
+    case 6: return launch_n3<EVP, 3, false>(h, A);
+    default: return launch_n3<EVP, 3, true>(h, A);
+  }
+}
+
+}  // namespace
+
+// Newton-3 path: the fast-path forms of mmm_pair.cu plus EV switched on (its prefactor is the
+// unit of the accumulators).
+bool mmm_pair_n3_eligible(const mmm_system* h) {
+  if (!mmm_pair_fast_path(h)) return false;
+  if (h->pp.ev_form != MMM_EV_POWERLAW) return false;
+  if (!(h->pp.ev_eps > 0.0f) || !(h->pp.ev_sigma > 0.0f)) return false;
+  return true;
+}
+
+int64_t mmm_n3_jstages(const mmm_system* h) { return h->npad / N3_JB; }
+
+// Work items: for every i-block, runs of cj j-stages starting at the diagonal.
+int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, int* cj_out) {
+  const int64_t nib = h->npad / N3_IB, njs = h->npad / N3_JB;
+  int64_t pairs = 0;
+  for (int64_t i = 0; i < nib; ++i) pairs += njs - 2 * i;
+  const int64_t target_items = (int64_t)h->sm_count * 2 * 48;
+  int64_t cj = pairs / target_items;
+  cj = cj < 1 ? 1 : (cj > 16 ? 16 : cj);
+  items.clear();
+  for (int64_t i = 0; i < nib; ++i)
+    for (int64_t js = 2 * i; js < njs; js += cj) items.push_back(make_int2((int)i, (int)js));
+  *cj_out = (int)cj;
+  return MMM_OK;
+}
+
+int mmm_launch_pair_n3(mmm_system* h, const int* d_skip) {
+  const PairParams& p = h->pp;
+  N3Args A;
+  A.pos4 = h->d_pos4;
+  A.tiles = h->d_tiles;
+  A.facc = h->d_facc;
+  A.epair = h->d_epair;
+  A.items = h->d_items;
+  A.counter = h->d_counter;
+  A.skip = d_skip;
+  A.npad = h->npad;
+  A.n_items = (int)h->n_items;
+  A.n_jstages = (int)(h->npad / N3_JB);
+  A.cj = h->n3_cj;
+  // U = p eps sigma^p in double, from the float parameters the gather kernel uses too
+  const double U = (double)p.ev_power * (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
+  A.fscale = U * N3_FIXED;
+  A.e_ev = (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
+  N3Consts& c = A.c;
+  c.ev_rs = p.ev_rs;
+  c.g_c = p.g_c;
+  c.rg2 = p.rg2;
+  c.chb_kc = p.chb_kc;
+  c.chb_c = p.chb_form >= 0 ? (float)((double)p.chb_de / U) : 0.0f;
+  c.gk = (p.scb_form >= 0 ? 1 : 0) | (p.cob_form >= 0 ? 2 : 0);
+  const double rc = p.scb_form >= 0 ? p.scb_rc : p.cob_rc;
+  const double inv = rc > 0.0 ? 1.0 / (rc * rc * U) : 0.0;
+  // s + 2 = 0..4 <-> s = -2..2 ; scb_e = {Ea1 (s=2), Ea2 (s=1), Eb1 (s=-1), Eb2 (s=-2)}
+  c.a_scb[0] = (float)(p.scb_e[3] * inv);
+  c.a_scb[1] = (float)(p.scb_e[2] * inv);
+  c.a_scb[2] = 0.0f;
+  c.a_scb[3] = (float)(p.scb_e[1] * inv);
+  c.a_scb[4] = (float)(p.scb_e[0] * inv);
+  c.a_cob[0] = 0.0f;
+  c.a_cob[1] = (float)(p.cob_ea * inv);
+  c.a_cob[2] = (float)(p.cob_eb * inv);
+  c.a_cob[3] = 0.0f;
+  A.e_gauss = -(rc * rc) * U;
+  A.e_chb = (double)p.chb_de;
+
+  MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
+  const bool collect = h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
+  cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
+  cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
+  if (collect) h->ev_cursor++;
+  MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+  const bool chb = p.chb_form >= 0;
+  if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
+  else launch_n3_evp<3>(h, A, c.gk, chb);
+  h->launches++;
+  MMM_CUDA(h, cudaGetLastError());
+  MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  return MMM_OK;
+}

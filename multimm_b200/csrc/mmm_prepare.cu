@@ -19,14 +19,15 @@ __global__ void __launch_bounds__(256) k_prepare(const double* __restrict__ x,
   const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t i = tile * MMM_TILE + lane;
   if (i >= npad) return;
-  float px = MMM_PAD_COORD, py = MMM_PAD_COORD, pz = MMM_PAD_COORD;
-  int ty = mmm_pack_type(0, MMM_PAD_CHROM);
   const bool real = i < n;
+  float px, py, pz;
+  const int ty = type[i];  // pads carry their own unique chromosome id (mmm_internal.cuh)
   if (real) {
     px = (float)(x[3 * i] - center[0]);
     py = (float)(x[3 * i + 1] - center[1]);
     pz = (float)(x[3 * i + 2] - center[2]);
-    ty = type[i];
+  } else {
+    px = py = pz = MMM_PAD_COORD + MMM_PAD_STEP * (float)(i - n);
   }
   pos4[i] = make_float4(px, py, pz, __int_as_float(ty));
 
@@ -36,8 +37,8 @@ __global__ void __launch_bounds__(256) k_prepare(const double* __restrict__ x,
   float hix = real ? px : -big, hiy = real ? py : -big, hiz = real ? pz : -big;
   int ch = (ty >> 8) & 0xFFFF;
   int cmin = real ? ch : 0x7fffffff, cmax = real ? ch : -1;
-  // a tile that mixes real and padding beads must never be treated as single-chromosome:
-  // the padding id widens its range so the pair kernel keeps the per-pair comparison
+  // bounding box and chromosome range cover the REAL beads only; a tile that mixes real and
+  // padding beads gets cmax = a pad id, so it is never treated as single-chromosome
   const bool mixed = __any_sync(0xffffffffu, real) && !__all_sync(0xffffffffu, real);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

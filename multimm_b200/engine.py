@@ -166,6 +166,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.mmm_launch_count(self._h))
 
+    def set_pair_kernel(self, which: int):
+        """0 = automatic (Newton-3 kernel for the default forms), 1 = always the gather kernel."""
+        self._ck(self._lib.mmm_set_pair_kernel(self._h, int(which)))
+
+    @property
+    def pair_kernel_in_use(self) -> int:
+        """0 none, 1 gather, 2 Newton-3, 3 cut-off cell list (kernel of the last evaluation)."""
+        return int(self._lib.mmm_pair_kernel_in_use(self._h))
+
     @property
     def last_pair_kernel_ms(self) -> float:
         ms = C.c_float()
