@@ -187,6 +187,11 @@ int mmm_last_pair_kernel_ms(mmm_handle h, float *ms_out);
 /* Cell-list contents of the last cutoff-mode evaluation (bit-exact parity): sorted bead
  * order (int32[N]) and the cell key of each sorted bead (uint32[N]). */
 int mmm_get_cell_list(mmm_handle h, int32_t *order_out, uint32_t *key_out);
+/* Grid of that cell list (cell edge >= cut-off, cells per axis, common origin of the centred FP32
+ * coordinates) and the number of unordered pairs with r2 < rc^2 the pair kernel found: with these
+ * the oracle rebuilds keys, order and the neighbour count bit for bit. Any output may be NULL. */
+int mmm_get_cell_grid(mmm_handle h, float *cell_out, int32_t *dim_out, float *origin_out,
+                      int64_t *pairs_in_cutoff);
 /* Micro-benchmarks that measure this GPU's FP32-FMA and MUFU peaks (the roofline
  * denominators of the pair kernel; MEASURED_PEAKS.json has only HBM and bf16). */
 int mmm_measure_fp32_peak(int device, double *tflops_out, double *mufu_tops_out);

@@ -32,7 +32,7 @@ EXPORTS = (
     "mmm_set_positions", "mmm_get_positions", "mmm_set_positions_device", "mmm_get_positions_device",
     "mmm_hilbert_init", "mmm_hilbert_points",
     "mmm_energy_forces", "mmm_energy_forces_device", "mmm_evaluate_n", "mmm_evaluate_timed", "mmm_minimize",
-    "mmm_launch_count", "mmm_set_pair_kernel", "mmm_pair_kernel_in_use", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_measure_fp32_peak",
+    "mmm_launch_count", "mmm_set_pair_kernel", "mmm_pair_kernel_in_use", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_get_cell_grid", "mmm_measure_fp32_peak",
 )
 
 
@@ -95,6 +95,7 @@ def load():
         "mmm_pair_kernel_in_use": (i32, [vp]),
         "mmm_last_pair_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "mmm_get_cell_list": (i32, [vp, vp, vp]),
+        "mmm_get_cell_grid": (i32, [vp, C.POINTER(C.c_float), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(i64)]),
         "mmm_measure_fp32_peak": (i32, [i32, C.POINTER(dbl), C.POINTER(dbl)]),
     }
     for name, (res, args) in sigs.items():

@@ -125,7 +125,7 @@ int mmm_destroy(mmm_handle h) {
                   h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_tiles, h->d_g,
                   h->d_fpair, h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
-                  h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp};
+                  h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_done) cudaFreeHost(h->h_done);
@@ -408,7 +408,8 @@ static void free_scratch(mmm_system* h) {
 // Size the pair-kernel work decomposition and its scratch for the kernel that will run.
 static int ensure_scratch(mmm_system* h) {
   const int mode = wanted_pair_mode(h);
-  if (h->scratch_sig == mode) return MMM_OK;
+  const int sig = mode * 2 + (mode == 3 && h->pp.chb_form >= 0 ? 1 : 0);
+  if (h->scratch_sig == sig) return MMM_OK;
   free_scratch(h);
   h->pair_mode = mode;
   int rc;
@@ -423,18 +424,15 @@ static int ensure_scratch(mmm_system* h) {
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
     if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
     MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
-  } else if (mode == 3) {
-    h->n_items = mmm_cells_energy_slots(h);
-    h->nchunk = 1;
-    if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
-    MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
   } else {
     // gather kernel: items = i-blocks x j-chunks, enough of them that the dynamic scheduler keeps
     // every SM busy to the end; one partial-force plane per chunk
     const int64_t niblk = h->npad / MMM_IBLOCK;
     const int64_t stages = h->ntiles / (MMM_STAGE / MMM_TILE);
     int64_t nchunk = 1;
-    if (mode == 1) {
+    // cut-off mode with CHB on: an exact CHB-only gather pass runs beside the cell-list pass
+    const bool exact_pass = mode == 1 || (mode == 3 && h->pp.chb_form >= 0);
+    if (exact_pass) {
       const int64_t target = (int64_t)h->sm_count * 4 * 6;  // ~6 items per resident CTA
       nchunk = (target + niblk - 1) / niblk;
       nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, std::min<int64_t>(stages, 64)));
@@ -445,14 +443,23 @@ static int ensure_scratch(mmm_system* h) {
     h->nchunk = (int)nchunk;
     h->chunk_tiles = (int)((stages + nchunk - 1) / nchunk) * (MMM_STAGE / MMM_TILE);
     h->n_items = niblk * nchunk;
-    if (mode == 1) {
-      if ((rc = dev_alloc(h, &h->d_fpair, (size_t)nchunk * 3 * (size_t)h->npad))) return rc;
-      MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * (size_t)nchunk * 3 * (size_t)h->npad, h->stream));
+    int64_t planes = exact_pass ? nchunk : 0;
+    if (!exact_pass) h->n_items = mode == 3 ? 0 : 1;
+    if (mode == 3) {
+      h->cells_plane = (int)planes;
+      h->cells_item0 = h->n_items;
+      planes += 1;
+      h->n_items += mmm_cells_energy_slots(h);
+    }
+    h->n_planes = (int)planes;
+    if (planes > 0) {
+      if ((rc = dev_alloc(h, &h->d_fpair, (size_t)planes * 3 * (size_t)h->npad))) return rc;
+      MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * (size_t)planes * 3 * (size_t)h->npad, h->stream));
     }
   }
   if ((rc = dev_alloc(h, &h->d_epair, (size_t)h->n_items * 4))) return rc;
   MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
-  h->scratch_sig = mode;
+  h->scratch_sig = sig;
   return MMM_OK;
 }
 
@@ -461,8 +468,15 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
   if (h->topo_dirty && (rc = mmm_upload_topology(h))) return rc;
   if ((rc = ensure_scratch(h))) return rc;
   if ((rc = mmm_launch_prepare(h, d_skip))) return rc;
-  if (h->pair_mode == 3) rc = mmm_launch_pair_cutoff(h, d_skip);
-  else if (h->pair_mode == 2) rc = mmm_launch_pair_n3(h, d_skip);
+  if (h->pair_mode == 3) {
+    if (h->pp.chb_form >= 0) {
+      PairParams only_chb = h->pp;
+      only_chb.ev_form = only_chb.cob_form = only_chb.scb_form = MMM_FORM_OFF;
+      only_chb.cutoff2 = 0.0f;
+      if ((rc = mmm_launch_pair_exact(h, d_skip, &only_chb))) return rc;
+    }
+    rc = mmm_launch_pair_cutoff(h, d_skip);
+  } else if (h->pair_mode == 2) rc = mmm_launch_pair_n3(h, d_skip);
   else if (h->pair_mode == 1) rc = mmm_launch_pair_exact(h, d_skip);
   if (rc) return rc;
   return mmm_launch_assemble(h, d_skip);

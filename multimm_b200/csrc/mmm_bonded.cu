@@ -322,9 +322,9 @@ int mmm_upload_angles(mmm_system* h, const int32_t* ai, const int32_t* aj, const
 int mmm_launch_assemble(mmm_system* h, const int* d_skip) {
   AsmArgs A;
   A.x = h->d_x;
-  A.fpair = h->pair_mode == 1 ? h->d_fpair : nullptr;
+  A.fpair = (h->pair_mode == 1 || h->pair_mode == 3) ? h->d_fpair : nullptr;
   A.facc = h->pair_mode == 2 ? h->d_facc : nullptr;
-  A.nchunk = h->nchunk;
+  A.nchunk = h->n_planes;
   A.n = h->n;
   A.npad = h->npad;
   A.bl_ptr = h->d_bl_ptr; A.bl_partner = h->d_bl_partner; A.bl_flags = h->d_bl_flags;

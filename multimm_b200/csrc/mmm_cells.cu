@@ -1,21 +1,322 @@
-// mmm_cells.cu — cutoff mode (opt-in, mmm_set_cutoff(rc > 0)): cell-list build and the pair
-// kernel over neighbouring cells.  The reference itself never sets a cutoff (NoCutoff), so this
-// path is an extension whose oracle applies the same truncation.
+// mmm_cells.cu — cut-off mode (opt-in, mmm_set_cutoff(rc > 0)): Morton-sorted cell list and the
+// pair kernel over neighbouring cells, for sm_100a.
 //
-// Round-1 status: not built yet.  The entry points exist so the ABI is complete; they report
-// MMM_ERR_STATE instead of silently falling back to anything.
+// The reference itself never sets a cut-off (every CustomNonbondedForce stays at NoCutoff,
+// model.py:181,231,307,397), so this path is the north star's "pair interactions over a cell list"
+// as an explicit extension: plain truncation (OpenMM CutoffNonPeriodic semantics, no shift, no
+// switch) of EV / COB / SCB at r < rc; the oracle applies the same truncation with the same FP32
+// inclusion test, so cell contents, sorted order and the number of pairs inside the cut-off are
+// bit-exact (tests/test_gpu_parity.py).  CHB's polynomial grows with r and cannot be truncated:
+// when CHB is on, an exact all-pairs pass restricted to CHB runs beside the cell-list pass.
+//
+// Per evaluation
+//   k_cell_grid   (1 block)  bounding box of the real tiles -> origin, cell edge (>= rc), dim <= 64
+//   k_cell_keys   (HBM: 16 B read + 8 B written per bead)   30-bit Morton key of the bead's cell
+//   CUB radix sort of (key, bead id) pairs, 30 key bits, stable => order is (key, id)
+//   k_cell_ranges (HBM: 8 + 16 B read, 16 + <=8 B written)  sorted float4 copy + [start, end) per cell
+//   k_pair_cells  one warp per cell: lanes hold up to 32 i-beads of the cell, all lanes walk the
+//                 same j-list (the 27 neighbouring cells, fixed order, broadcast loads), gather
+//                 formulation => fixed summation order, no atomics.  FP32 inside a neighbour cell,
+//                 FP64 across cells.  Every form of every term is supported (pairmath::pair_generic).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "mmm_internal.cuh"
+#include "mmm_pairmath.cuh"
 
-int64_t mmm_cells_energy_slots(const mmm_system* h) { (void)h; return 1; }
+namespace {
 
+using namespace pairmath;
+
+constexpr int kMaxDim = 64;
+constexpr int kMaxCodes = kMaxDim * kMaxDim * kMaxDim;  // 8^6
+constexpr int kCellWarps = 8;
+
+struct CellGrid {
+  float origin, cell;
+  int dim, bits;
+};
+
+__host__ __device__ inline uint32_t spread3(uint32_t v) {
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000FF;
+  v = (v | (v << 8)) & 0x0300F00F;
+  v = (v | (v << 4)) & 0x030C30C3;
+  v = (v | (v << 2)) & 0x09249249;
+  return v;
+}
+__host__ __device__ inline uint32_t compact3(uint32_t v) {
+  v &= 0x09249249;
+  v = (v | (v >> 2)) & 0x030C30C3;
+  v = (v | (v >> 4)) & 0x0300F00F;
+  v = (v | (v >> 8)) & 0x030000FF;
+  v = (v | (v >> 16)) & 0x3ff;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_cell_grid(const TileInfo* __restrict__ tiles, int ntiles, float rc,
+                                                   CellGrid* __restrict__ g, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ float s_lo[256], s_hi[256];
+  float lo = 3.0e38f, hi = -3.0e38f;
+  for (int t = threadIdx.x; t < ntiles; t += 256) {
+    const TileInfo ti = tiles[t];
+    if (ti.cmin >= MMM_PAD_CHROM) continue;  // padding only
+    lo = fminf(lo, fminf(ti.lox, fminf(ti.loy, ti.loz)));
+    hi = fmaxf(hi, fmaxf(ti.hix, fmaxf(ti.hiy, ti.hiz)));
+  }
+  s_lo[threadIdx.x] = lo;
+  s_hi[threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_lo[threadIdx.x] = fminf(s_lo[threadIdx.x], s_lo[threadIdx.x + o]);
+      s_hi[threadIdx.x] = fmaxf(s_hi[threadIdx.x], s_hi[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float origin = s_lo[0];
+    const float extent = fmaxf(s_hi[0] - origin, 0.0f);
+    float cell = rc;
+    int dim = (int)floorf(__fdiv_rn(extent, cell)) + 1;
+    if (dim > kMaxDim) {  // coarser cells are still correct (cell >= rc); keys are clamped anyway
+      cell = __fdiv_rn(extent, (float)(kMaxDim - 1));
+      dim = kMaxDim;
+    }
+    int bits = 0;
+    while ((1 << bits) < dim) ++bits;
+    g->origin = origin;
+    g->cell = cell;
+    g->dim = dim;
+    g->bits = bits;
+  }
+}
+
+__device__ __forceinline__ uint32_t cell_coord(float x, const CellGrid& g) {
+  int v = (int)floorf(__fdiv_rn(x - g.origin, g.cell));
+  v = v < 0 ? 0 : v;
+  v = v > g.dim - 1 ? g.dim - 1 : v;
+  return (uint32_t)v;
+}
+
+__global__ void __launch_bounds__(256) k_cell_keys(const float4* __restrict__ pos4, int64_t n,
+                                                   const CellGrid* __restrict__ gp, uint32_t* __restrict__ keys,
+                                                   int* __restrict__ ids, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const CellGrid g = *gp;
+  const float4 p = pos4[i];
+  keys[i] = spread3(cell_coord(p.x, g)) | (spread3(cell_coord(p.y, g)) << 1) | (spread3(cell_coord(p.z, g)) << 2);
+  ids[i] = (int)i;
+}
+
+__global__ void __launch_bounds__(256) k_cell_ranges(const float4* __restrict__ pos4, int64_t n,
+                                                     const uint32_t* __restrict__ keys, const int* __restrict__ order,
+                                                     float4* __restrict__ pos4s, int* __restrict__ cstart,
+                                                     int* __restrict__ cend, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t k = keys[s];
+  pos4s[s] = pos4[order[s]];
+  if (s == 0 || keys[s - 1] != k) cstart[k] = (int)s;
+  if (s == n - 1 || keys[s + 1] != k) cend[k] = (int)s + 1;
+}
+
+struct CellArgs {
+  const float4* pos4s;
+  const int* order;
+  const int* cstart;
+  const int* cend;
+  const CellGrid* grid;
+  double* fplane;   // [3][npad], indexed by ORIGINAL bead id
+  double* epair;    // [n_cell_items][4]
+  unsigned long long* npairs;  // [n_cell_items] ordered pairs inside the cut-off
+  int64_t npad;
+  const int* skip;
+  PairParams pp;    // CHB switched off (handled by the exact pass)
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kCellWarps * 32) k_pair_cells(const CellArgs A) {
+  __shared__ double s_red[5][kCellWarps];
+  if (A.skip && *A.skip) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const CellGrid g = *A.grid;
+  const PairParams& c = A.pp;
+  const uint32_t code = blockIdx.x * kCellWarps + warp;
+  double de[4] = {0.0, 0.0, 0.0, 0.0};
+  unsigned long long cnt = 0;
+  int s0 = 0, s1 = 0;
+  if (code < (1u << (3 * g.bits))) { s0 = A.cstart[code]; s1 = A.cend[code]; }
+  if (s1 > s0) {
+    const int cx = (int)compact3(code), cy = (int)compact3(code >> 1), cz = (int)compact3(code >> 2);
+    for (int base = s0; base < s1; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < s1;
+      const float4 pi = A.pos4s[valid ? i : s0];
+      const int oi = A.order[valid ? i : s0];
+      IBead b;
+      b.x = pi.x; b.y = pi.y; b.z = pi.z; b.w = __float_as_int(pi.w);
+      b.a_scb = 0.0f; b.a_cob = 0.0f;
+      const int si = (b.w & 7) - 2;
+      double dfx = 0.0, dfy = 0.0, dfz = 0.0;
+      for (int nz = cz - 1; nz <= cz + 1; ++nz) {
+        if (nz < 0 || nz >= g.dim) continue;
+        for (int ny = cy - 1; ny <= cy + 1; ++ny) {
+          if (ny < 0 || ny >= g.dim) continue;
+          for (int nx = cx - 1; nx <= cx + 1; ++nx) {
+            if (nx < 0 || nx >= g.dim) continue;
+            const uint32_t nc = spread3((uint32_t)nx) | (spread3((uint32_t)ny) << 1) | (spread3((uint32_t)nz) << 2);
+            const int j0 = A.cstart[nc], j1 = A.cend[nc];
+            float fx = 0.f, fy = 0.f, fz = 0.f, e4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = j0; j < j1; ++j) {
+              const float4 pj = A.pos4s[j];
+              const int oj = A.order[j];
+              const bool in = pair_generic(pj, b, si, oi < oj, c, valid && j != i, fx, fy, fz, e4, c.cutoff2);
+              cnt += in ? 1ull : 0ull;
+            }
+            dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
+            de[0] += (double)e4[0]; de[1] += (double)e4[1]; de[2] += (double)e4[2]; de[3] += (double)e4[3];
+          }
+        }
+      }
+      if (valid) {
+        A.fplane[oi] = dfx;
+        A.fplane[(size_t)A.npad + oi] = dfy;
+        A.fplane[2 * (size_t)A.npad + oi] = dfz;
+      }
+    }
+  }
+  // each unordered pair was seen from both sides
+  double v[5] = {0.5 * de[0], 0.5 * de[1], 0.5 * de[2], 0.5 * de[3], (double)cnt};
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    v[q] = warp_sum_d(v[q]);
+    if (lane == 0) s_red[q][warp] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kCellWarps; ++w) s += s_red[threadIdx.x][w];
+    if (threadIdx.x < 4) A.epair[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+    else A.npairs[blockIdx.x] = (unsigned long long)(s + 0.5);
+  }
+}
+
+}  // namespace
+
+int64_t mmm_cells_energy_slots(const mmm_system* h) {
+  (void)h;
+  return kMaxCodes / kCellWarps;
+}
+
+int mmm_cells_alloc(mmm_system* h) {
+  if (h->d_keys) return MMM_OK;
+  const size_t n = (size_t)h->n;
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_keys, n * sizeof(uint32_t)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_keys_tmp, n * sizeof(uint32_t)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_order, n * sizeof(int)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_order_tmp, n * sizeof(int)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_pos4_sorted, n * sizeof(float4)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_start, (size_t)2 * kMaxCodes * sizeof(int)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_grid, sizeof(CellGrid)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_npairs, (size_t)(kMaxCodes / kCellWarps) * sizeof(unsigned long long)));
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->d_keys_tmp, h->d_keys, h->d_order_tmp, h->d_order, (int)n, 0, 30,
+                                  h->stream);
+  h->sort_tmp_bytes = bytes;
+  MMM_CUDA(h, cudaMalloc(&h->d_sort_tmp, bytes));
+  return MMM_OK;
+}
+
+// Cell-list pass: EV / COB / SCB truncated at the cut-off, forces into plane `plane` of d_fpair,
+// energies into d_epair at item offset `item0`.
 int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
-  (void)d_skip;
-  return mmm_fail(h, MMM_ERR_STATE, "cutoff mode is not available in this build; use mmm_set_cutoff(h, 0)");
+  int rc;
+  if ((rc = mmm_cells_alloc(h))) return rc;
+  const int n = (int)h->n;
+  const int blocks = (n + 255) / 256;
+  CellGrid* grid = reinterpret_cast<CellGrid*>(h->d_cell_grid);
+  int* cstart = h->d_cell_start;
+  int* cend = h->d_cell_start + kMaxCodes;
+
+  const bool collect = h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
+  cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
+  cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
+  if (collect) h->ev_cursor++;
+  MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+
+  MMM_CUDA(h, cudaMemsetAsync(h->d_cell_start, 0, (size_t)2 * kMaxCodes * sizeof(int), h->stream));
+  k_cell_grid<<<1, 256, 0, h->stream>>>(h->d_tiles, (int)h->ntiles, (float)h->cutoff, grid, d_skip);
+  k_cell_keys<<<blocks, 256, 0, h->stream>>>(h->d_pos4, h->n, grid, h->d_keys_tmp, h->d_order_tmp, d_skip);
+  size_t bytes = h->sort_tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, bytes, h->d_keys_tmp, h->d_keys, h->d_order_tmp, h->d_order, n, 0, 30,
+                                  h->stream);
+  k_cell_ranges<<<blocks, 256, 0, h->stream>>>(h->d_pos4, h->n, h->d_keys, h->d_order, h->d_pos4_sorted, cstart, cend,
+                                               d_skip);
+  CellArgs A;
+  A.pos4s = h->d_pos4_sorted;
+  A.order = h->d_order;
+  A.cstart = cstart;
+  A.cend = cend;
+  A.grid = grid;
+  A.fplane = h->d_fpair + (size_t)h->cells_plane * 3 * (size_t)h->npad;
+  A.epair = h->d_epair + (size_t)h->cells_item0 * 4;
+  A.npairs = h->d_cell_npairs;
+  A.npad = h->npad;
+  A.skip = d_skip;
+  A.pp = h->pp;
+  A.pp.chb_form = MMM_FORM_OFF;
+  k_pair_cells<<<kMaxCodes / kCellWarps, kCellWarps * 32, 0, h->stream>>>(A);
+  h->launches += 5;  // + the radix-sort kernels of CUB (library), not counted
+  MMM_CUDA(h, cudaGetLastError());
+  MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  return MMM_OK;
 }
 
-extern "C" int mmm_get_cell_list(mmm_handle h, int32_t* order_out, uint32_t* key_out) {
-  (void)order_out;
-  (void)key_out;
+extern "C" {
+
+int mmm_get_cell_list(mmm_handle h, int32_t* order_out, uint32_t* key_out) {
   if (!h) return MMM_ERR_ARG;
-  return mmm_fail(h, MMM_ERR_STATE, "cutoff mode is not available in this build");
+  if (h->pair_mode != 3 || !h->d_keys)
+    return mmm_fail(h, MMM_ERR_STATE, "mmm_get_cell_list: no cut-off evaluation has run on this handle");
+  cudaSetDevice(h->device);
+  if (order_out)
+    MMM_CUDA(h, cudaMemcpyAsync(order_out, h->d_order, sizeof(int) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (key_out)
+    MMM_CUDA(h, cudaMemcpyAsync(key_out, h->d_keys, sizeof(uint32_t) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMM_OK;
 }
+
+int mmm_get_cell_grid(mmm_handle h, float* cell_out, int32_t* dim_out, float* origin_out, int64_t* pairs_in_cutoff) {
+  if (!h) return MMM_ERR_ARG;
+  if (h->pair_mode != 3 || !h->d_keys)
+    return mmm_fail(h, MMM_ERR_STATE, "mmm_get_cell_grid: no cut-off evaluation has run on this handle");
+  cudaSetDevice(h->device);
+  CellGrid g;
+  std::vector<unsigned long long> cnt((size_t)(kMaxCodes / kCellWarps));
+  MMM_CUDA(h, cudaMemcpyAsync(&g, h->d_cell_grid, sizeof(g), cudaMemcpyDeviceToHost, h->stream));
+  MMM_CUDA(h, cudaMemcpyAsync(cnt.data(), h->d_cell_npairs, cnt.size() * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (cell_out) *cell_out = g.cell;
+  if (dim_out) *dim_out = g.dim;
+  if (origin_out) *origin_out = g.origin;
+  if (pairs_in_cutoff) {
+    unsigned long long s = 0;
+    for (unsigned long long v : cnt) s += v;
+    *pairs_in_cutoff = (int64_t)(s / 2);  // the gather kernel sees each unordered pair twice
+  }
+  return MMM_OK;
+}
+
+}  // extern "C"

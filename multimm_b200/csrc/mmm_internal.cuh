@@ -140,6 +140,7 @@ struct mmm_system {
 
   // pair-kernel scratch
   int nchunk = 1;
+  int n_planes = 0;              // planes of d_fpair the assemble pass sums (gather chunks + cell-list plane)
   int chunk_tiles = 0;           // j-tiles per chunk (a whole number of stages)
   int scratch_sig = -1;
   double* d_fpair = nullptr;     // [nchunk][3][npad]
@@ -176,8 +177,10 @@ struct mmm_system {
   int* d_cell_start = nullptr;   // [ncells+1]
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
-  int cell_dim = 0;
-  float cell_size = 0.f, cell_origin = 0.f;
+  void* d_cell_grid = nullptr;   // device CellGrid {origin, cell, dim, bits}
+  unsigned long long* d_cell_npairs = nullptr;  // ordered pairs inside the cut-off, per CTA
+  int cells_plane = 0;           // plane of d_fpair the cell-list pass writes
+  int64_t cells_item0 = 0;       // first d_epair item of the cell-list pass
 
   // timing
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
@@ -206,8 +209,9 @@ int mmm_fail(mmm_system* h, int code, const std::string& msg);
 int mmm_launch_prepare(mmm_system* h, const int* d_skip);  // d_x -> d_pos4, d_tiles
 int mmm_launch_hilbert(mmm_system* h, int p, double spacing, int32_t* d_ijk);
 // mmm_pair.cu
-int mmm_launch_pair_exact(mmm_system* h, const int* d_skip);  // d_pos4 -> d_fpair, d_epair
+int mmm_launch_pair_exact(mmm_system* h, const int* d_skip, const PairParams* pp_override = nullptr);  // d_pos4 -> d_fpair, d_epair
 bool mmm_pair_fast_path(const mmm_system* h);
+bool mmm_pair_fast_path_pp(const PairParams& p);
 // mmm_pair_n3.cu
 bool mmm_pair_n3_eligible(const mmm_system* h);
 int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, int* cj_out);

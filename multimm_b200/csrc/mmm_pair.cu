@@ -20,31 +20,13 @@
 // The roofline that bounds this kernel is the FP32-FMA / MUFU issue rate, not HBM: a stage of
 // 4 KB is reused by 256 threads x 256 pairs.
 #include "mmm_internal.cuh"
+#include "mmm_pairmath.cuh"
 
 namespace {
 
-enum : int { PM_GAUSS = 1, PM_CHB = 2, PM_CHBMASK = 4, PM_SELF = 8 };
+using namespace pairmath;
 
-__device__ __forceinline__ float fast_rcp(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_lg2(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_rsqrt(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+enum : int { PM_GAUSS = 1, PM_CHB = 2, PM_CHBMASK = 4, PM_SELF = 8 };
 
 template <int P>
 __device__ __forceinline__ float powi(float w) {
@@ -57,21 +39,6 @@ __device__ __forceinline__ float powi(float w) {
     return w * powi<P - 1>(w);
   }
 }
-
-// per-thread constants of the i-bead
-struct IBead {
-  float x, y, z;
-  int w;
-  float a_scb, a_cob;  // eps_i / rc^2 for the SCB / COB Gaussian (0 when the bead's label has none)
-};
-
-struct Acc {
-  float fx, fy, fz;     // force with all prefactors applied (everything except far EV)
-  float ux, uy, uz;     // EV force in units of p * eps * sigma^p (far tiles)
-  float eev;            // sum w^p            (x eps sigma^p)
-  float gscb, gcob;     // sum of matching Gaussians (x eps_i)
-  float echb;           // sum r^2 (kC r^2 - r + 1) over same-chromosome pairs (x dE)
-};
 
 // One tile of 32 j-beads against this thread's i-bead.  EVP: integer EV power; GK: 0 none,
 // 1 SCB, 2 COB, 3 both Gaussian block terms.
@@ -145,95 +112,6 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ sj, const I
       a.uy = fmaf(fs, dy, a.uy);
       a.uz = fmaf(fs, dz, a.uz);
     }
-  }
-}
-
-// Generic pair: any functional form, runtime switches, no tile skipping.  Used for the
-// non-default forms (model.py:205-211, 258-288, 338-378, 424-445) and non-integer EV powers.
-__device__ __forceinline__ void pair_generic(const float4 pj, const IBead& b, const int si,
-                                             const bool i_lower, const PairParams& c, bool live,
-                                             float& fx, float& fy, float& fz, float e4[4]) {
-  const float dx = b.x - pj.x, dy = b.y - pj.y, dz = b.z - pj.z;
-  float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  if (!live) r2 = 1.0f;
-  const float inv_r = fast_rsqrt(r2);
-  const float r = r2 * inv_r;
-  const int wj = __float_as_int(pj.w);
-  const int sj = (wj & 7) - 2;
-  float dedr = 0.0f;  // dE/dr summed over terms
-  float e[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c.ev_form == MMM_EV_POWERLAW) {
-    const float w = fast_rcp(r + c.ev_rs);
-    const float en = c.ev_eps * fast_ex2(c.ev_power * fast_lg2(c.ev_sigma * w));
-    e[0] = en;
-    dedr -= c.ev_power * en * w;
-  } else if (c.ev_form == MMM_EV_GAUSSIAN_CORE) {
-    const float is2 = 1.0f / (c.ev_sigma * c.ev_sigma);
-    const float en = c.ev_eps * fast_ex2(-0.72134752f * r2 * is2);
-    e[0] = en;
-    dedr -= en * r * is2;
-  }
-  if (c.cob_form >= 0) {
-    const bool ai = si > 0, bi = si < 0, aj = sj > 0, bj = sj < 0;
-    float E;
-    if (c.cob_form == MMM_BLOCK_YUKAWA) {
-      // model.py:262-266 uses s1 on both factors; particle 1 is the lower index [OpenMM]
-      const int s1 = i_lower ? si : sj;
-      E = s1 > 0 ? c.cob_ea : (s1 < 0 ? c.cob_eb : 0.0f);
-    } else {
-      E = (ai && aj) ? c.cob_ea : ((bi && bj) ? c.cob_eb : 0.0f);
-    }
-    if (c.cob_form == MMM_BLOCK_GAUSSIAN) {
-      const float irc2 = 1.0f / (c.cob_rc * c.cob_rc);
-      const float g = fast_ex2(-0.72134752f * r2 * irc2);
-      e[1] = -E * g;
-      dedr += E * g * r * irc2;
-    } else if (c.cob_form == MMM_BLOCK_YUKAWA) {
-      const float il = 1.0f / c.cob_rc;
-      const float g = fast_ex2(-1.44269504f * r * il);
-      e[1] = -E * g * inv_r;
-      dedr += E * g * (il * inv_r + inv_r * inv_r);
-    } else {
-      e[1] = (c.cob_rc - r >= 0.0f) ? -E : 0.0f;
-    }
-  }
-  if (c.scb_form >= 0) {
-    float E = 0.0f;
-    if (si == sj && si != 0) E = c.scb_e[si == 2 ? 0 : (si == 1 ? 1 : (si == -1 ? 2 : 3))];
-    if (c.scb_form == MMM_BLOCK_GAUSSIAN) {
-      const float irc2 = 1.0f / (c.scb_rc * c.scb_rc);
-      const float g = fast_ex2(-0.72134752f * r2 * irc2);
-      e[2] = -E * g;
-      dedr += E * g * r * irc2;
-    } else if (c.scb_form == MMM_BLOCK_YUKAWA) {
-      const float il = 1.0f / c.scb_rc;
-      const float g = fast_ex2(-1.44269504f * r * il);
-      e[2] = -E * g * inv_r;
-      dedr += E * g * (il * inv_r + inv_r * inv_r);
-    } else {
-      e[2] = (c.scb_rc - r >= 0.0f) ? -E : 0.0f;
-    }
-  }
-  if (c.chb_form >= 0 && ((b.w ^ wj) & 0xFFFF00) == 0) {
-    if (c.chb_form == MMM_CHB_POLYNOMIAL) {
-      e[3] = c.chb_de * r2 * fmaf(c.chb_kc, r2, 1.0f - r);
-      dedr += c.chb_de * r * fmaf(-3.0f, r, fmaf(4.0f * c.chb_kc, r2, 2.0f));
-    } else if (c.chb_form == MMM_CHB_GAUSSIAN) {
-      const float g = fast_ex2(-1.44269504f * c.chb_kc * r2);
-      e[3] = -c.chb_de * g;
-      dedr += 2.0f * c.chb_kc * r * c.chb_de * g;
-    } else {
-      const float q = fast_rcp(fmaf(c.chb_kc, r2, 1.0f));
-      e[3] = -c.chb_de * q;
-      dedr += c.chb_de * q * q * 2.0f * c.chb_kc * r;
-    }
-  }
-  if (live) {
-    const float fs = -dedr * inv_r;
-    fx = fmaf(fs, dx, fx);
-    fy = fmaf(fs, dy, fy);
-    fz = fmaf(fs, dz, fz);
-    e4[0] += e[0]; e4[1] += e[1]; e4[2] += e[2]; e4[3] += e[3];
   }
 }
 
@@ -420,8 +298,9 @@ int launch_evp(mmm_system* h, const PairArgs& A, int gk, bool chb) {
 
 // The specialised path covers the reference's default forms: power-law EV with an integer
 // power in {3, 6}, Gaussian COB/SCB sharing one range, polynomial CHB.
-bool mmm_pair_fast_path(const mmm_system* h) {
-  const PairParams& p = h->pp;
+bool mmm_pair_fast_path(const mmm_system* h) { return mmm_pair_fast_path_pp(h->pp); }
+
+bool mmm_pair_fast_path_pp(const PairParams& p) {
   if (p.ev_form != MMM_EV_POWERLAW) return false;
   if (!(p.ev_power == 6.0f || p.ev_power == 3.0f)) return false;
   if (p.cob_form != MMM_FORM_OFF && p.cob_form != MMM_BLOCK_GAUSSIAN) return false;
@@ -431,7 +310,9 @@ bool mmm_pair_fast_path(const mmm_system* h) {
   return true;
 }
 
-int mmm_launch_pair_exact(mmm_system* h, const int* d_skip) {
+// pp_override (cut-off mode): evaluate this parameter set instead of the handle's (the exact
+// CHB-only pass that runs beside the cell-list pass); no event timing in that case.
+int mmm_launch_pair_exact(mmm_system* h, const int* d_skip, const PairParams* pp_override) {
   PairArgs A;
   A.pos4 = h->d_pos4;
   A.tiles = h->d_tiles;
@@ -444,24 +325,25 @@ int mmm_launch_pair_exact(mmm_system* h, const int* d_skip) {
   A.ntiles = (int)h->ntiles;
   A.nchunk = h->nchunk;
   A.chunk_tiles = h->chunk_tiles;
-  A.n_items = (int)h->n_items;
-  A.pp = h->pp;
+  A.n_items = (int)((h->npad / MMM_IBLOCK) * h->nchunk);
+  A.pp = pp_override ? *pp_override : h->pp;
   MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
-  const bool collect = h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
+  const bool timed = pp_override == nullptr;
+  const bool collect = timed && h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
   cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
   cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
   if (collect) h->ev_cursor++;
-  MMM_CUDA(h, cudaEventRecord(ea, h->stream));
-  if (mmm_pair_fast_path(h)) {
-    const int gk = (h->pp.scb_form >= 0 ? 1 : 0) | (h->pp.cob_form >= 0 ? 2 : 0);
-    const bool chb = h->pp.chb_form >= 0;
-    if (h->pp.ev_power == 6.0f) launch_evp<6>(h, A, gk, chb);
+  if (timed) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+  if (mmm_pair_fast_path_pp(A.pp)) {
+    const int gk = (A.pp.scb_form >= 0 ? 1 : 0) | (A.pp.cob_form >= 0 ? 2 : 0);
+    const bool chb = A.pp.chb_form >= 0;
+    if (A.pp.ev_power == 6.0f) launch_evp<6>(h, A, gk, chb);
     else launch_evp<3>(h, A, gk, chb);
   } else {
     launch_variant<0, 0, false>(h, A);
   }
   h->launches++;
   MMM_CUDA(h, cudaGetLastError());
-  MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  if (timed) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
 }

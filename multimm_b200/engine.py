@@ -187,6 +187,12 @@ class Engine:
         self._ck(self._lib.mmm_get_cell_list(self._h, _p(order), _p(keys)))
         return order, keys
 
+    def cell_grid(self) -> dict:
+        """Grid of the last cut-off evaluation and the number of unordered pairs inside the cut-off."""
+        cell, dim, origin, pairs = C.c_float(), C.c_int(), C.c_float(), C.c_int64()
+        self._ck(self._lib.mmm_get_cell_grid(self._h, C.byref(cell), C.byref(dim), C.byref(origin), C.byref(pairs)))
+        return dict(cell=float(cell.value), dim=int(dim.value), origin=float(origin.value), pairs=int(pairs.value))
+
 
 def measure_fp32_peak(device: int = 0):
     """(FP32 TFLOP/s, MUFU Tera-op/s) measured by micro-benchmark on this GPU."""

@@ -125,6 +125,51 @@ def test_newton3_kernel_matches_gather_kernel(built_lib, n, n_chrom, terms):
     assert force_rel_err(f_n3, f_g) <= F_TOL
 
 
+@pytest.mark.parametrize("n,n_chrom,rc,terms", [
+    (3000, 2, 0.45, ("EV", "SCB", "BOND", "ANGLE")),
+    (8000, 3, 0.30, ("EV", "COB", "SCB", "SC", "LAM", "CF", "BOND", "LOOP", "ANGLE")),
+    (4000, 4, 0.60, ("EV", "SCB", "CHB", "BOND")),          # CHB is never truncated: exact pass beside the cells
+    (500, 1, 5.00, ("EV", "SCB")),                            # cut-off larger than the system: one cell
+])
+def test_cutoff_mode_cell_list(built_lib, n, n_chrom, rc, terms):
+    """Cut-off mode: Morton cell list bit-exact against the oracle's, same number of pairs inside the
+    cut-off, energies/forces at the usual bars against the oracle with the same truncation."""
+    case = make_case(n, n_chrom=n_chrom, seed=n + 1, terms=terms)
+    eng = to_engine(case, cutoff=rc)
+    e, f = eng.energy_forces()
+    assert eng.pair_kernel_in_use == 3
+    sysd = to_oracle(case, cutoff=rc)
+    e_ref, f_ref = O.energy_forces(sysd, case["x"])
+    for t in range(10):
+        assert abs(e[t] - e_ref[t]) <= E_TOL * max(abs(e_ref[t]), 1e-12) + 1e-9, (O.TERM_NAMES[t], e[t], e_ref[t])
+    assert force_rel_err(f, f_ref) <= F_TOL
+    # integer outputs: bit-exact
+    grid = eng.cell_grid()
+    assert grid["cell"] >= np.float32(rc) and 1 <= grid["dim"] <= 64
+    order, keys = eng.cell_list()
+    xc = (case["x"] - case["x"].mean(axis=0)).astype(np.float32)
+    keys_ref, order_ref = O.cell_list(xc, grid["cell"], grid["dim"], grid["origin"])
+    assert np.array_equal(order, order_ref)
+    assert np.array_equal(keys, keys_ref)
+    assert grid["pairs"] == O.count_pairs(sysd, case["x"])
+    # truncation really happened (fewer pairs than all-pairs) unless the cut-off spans the system
+    if rc < 1.0:
+        assert grid["pairs"] < n * (n - 1) // 2
+    e2, f2 = eng.energy_forces()
+    assert np.array_equal(e, e2) and np.array_equal(f, f2)
+    eng.close()
+
+
+def test_cutoff_mode_minimizes(built_lib):
+    case = make_case(2000, n_chrom=2, seed=21, terms=("EV", "SCB", "SC", "BOND", "LOOP", "ANGLE"))
+    eng = to_engine(case, cutoff=0.5)
+    rep = eng.minimize(tol=10.0, max_iter=40)
+    assert rep["e_final"] < rep["e_initial"] and np.isfinite(rep["e_final"])
+    e_chk = O.energy_forces(to_oracle(case, cutoff=0.5), eng.get_positions(), want_forces=False)[0].sum()
+    assert abs(e_chk - rep["e_final"]) <= 1e-5 * abs(e_chk)
+    eng.close()
+
+
 def test_translation_invariance(built_lib):
     case = make_case(4000, n_chrom=2, seed=10, terms=("EV", "SCB", "CHB", "BOND", "ANGLE", "LOOP"))
     eng = to_engine(case)
