@@ -11,6 +11,7 @@
 int mmm_launch_dots_decide(mmm_system* h);  // mmm_lbfgs.cu
 
 static thread_local std::string g_create_error;
+static void free_scratch(mmm_system* h);
 
 int mmm_fail(mmm_system* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -199,6 +200,9 @@ int mmm_set_bead_params(mmm_handle h, const int8_t* s, const int32_t* chrom, con
     ty[i] = mmm_pack_type(si, ci);
     sv[i] = (signed char)si;
   }
+  if (chrom) h->h_chrom.assign(chrom, chrom + h->n);
+  else h->h_chrom.clear();
+  if (h->scratch_sig >= 0) free_scratch(h);  // the CHB-only item list depends on the chromosome ids
   MMM_CUDA(h, cudaMemcpyAsync(h->d_type, ty.data(), sizeof(int) * ty.size(), cudaMemcpyHostToDevice, h->stream));
   MMM_CUDA(h, cudaMemcpyAsync(h->d_s, sv.data(), sv.size(), cudaMemcpyHostToDevice, h->stream));
   if (chrom_strength)
@@ -408,54 +412,59 @@ static void free_scratch(mmm_system* h) {
 // Size the pair-kernel work decomposition and its scratch for the kernel that will run.
 static int ensure_scratch(mmm_system* h) {
   const int mode = wanted_pair_mode(h);
-  const int sig = mode * 2 + (mode == 3 && h->pp.chb_form >= 0 ? 1 : 0);
+  const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0);
   if (h->scratch_sig == sig) return MMM_OK;
   free_scratch(h);
   h->pair_mode = mode;
   int rc;
-  if (mode == 2) {
+  // cut-off mode with CHB on: an exact CHB-only pass runs beside the cell-list pass — the Newton-3
+  // kernel over same-chromosome tile pairs for the polynomial form, the generic gather kernel else
+  const bool chb_n3 = mode == 3 && h->pp.chb_form == MMM_CHB_POLYNOMIAL;
+  const bool chb_gather = mode == 3 && h->pp.chb_form >= 0 && !chb_n3;
+  h->n_items = 0;
+  h->n3_items = 0;
+  h->n_planes = 0;
+  h->nchunk = 1;
+  if (mode == 2 || chb_n3) {
     // Newton-3: fixed-point force planes + work-item table
     std::vector<int2> items;
-    mmm_n3_build_items(h, items, &h->n3_cj);
-    h->n_items = (int64_t)items.size();
-    h->nchunk = 1;
+    mmm_n3_build_items(h, items, chb_n3);
+    h->n3_items = (int)items.size();
+    h->n3_chb_only = chb_n3;
+    h->n_items = h->n3_items;
     if ((rc = dev_alloc(h, &h->d_items, items.size()))) return rc;
     MMM_CUDA(h, cudaMemcpyAsync(h->d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
     if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
     MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
-  } else {
+  }
+  if (mode == 1 || chb_gather) {
     // gather kernel: items = i-blocks x j-chunks, enough of them that the dynamic scheduler keeps
     // every SM busy to the end; one partial-force plane per chunk
     const int64_t niblk = h->npad / MMM_IBLOCK;
     const int64_t stages = h->ntiles / (MMM_STAGE / MMM_TILE);
-    int64_t nchunk = 1;
-    // cut-off mode with CHB on: an exact CHB-only gather pass runs beside the cell-list pass
-    const bool exact_pass = mode == 1 || (mode == 3 && h->pp.chb_form >= 0);
-    if (exact_pass) {
-      const int64_t target = (int64_t)h->sm_count * 4 * 6;  // ~6 items per resident CTA
-      nchunk = (target + niblk - 1) / niblk;
-      nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, std::min<int64_t>(stages, 64)));
-      // chunks are whole stages; recompute the count so that no chunk is empty
-      const int64_t chunk_stages = (stages + nchunk - 1) / nchunk;
-      nchunk = (stages + chunk_stages - 1) / chunk_stages;
-    }
+    const int64_t target = (int64_t)h->sm_count * 4 * 6;  // ~6 items per resident CTA
+    int64_t nchunk = (target + niblk - 1) / niblk;
+    nchunk = std::max<int64_t>(1, std::min<int64_t>(nchunk, std::min<int64_t>(stages, 64)));
+    // chunks are whole stages; recompute the count so that no chunk is empty
+    const int64_t chunk_stages = (stages + nchunk - 1) / nchunk;
+    nchunk = (stages + chunk_stages - 1) / chunk_stages;
     h->nchunk = (int)nchunk;
     h->chunk_tiles = (int)((stages + nchunk - 1) / nchunk) * (MMM_STAGE / MMM_TILE);
     h->n_items = niblk * nchunk;
-    int64_t planes = exact_pass ? nchunk : 0;
-    if (!exact_pass) h->n_items = mode == 3 ? 0 : 1;
-    if (mode == 3) {
-      h->cells_plane = (int)planes;
-      h->cells_item0 = h->n_items;
-      planes += 1;
-      h->n_items += mmm_cells_energy_slots(h);
-    }
-    h->n_planes = (int)planes;
-    if (planes > 0) {
-      if ((rc = dev_alloc(h, &h->d_fpair, (size_t)planes * 3 * (size_t)h->npad))) return rc;
-      MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * (size_t)planes * 3 * (size_t)h->npad, h->stream));
-    }
+    h->n_planes = (int)nchunk;
+  }
+  if (mode == 3) {
+    h->cells_plane = h->n_planes;
+    h->cells_item0 = h->n_items;
+    h->n_planes += 1;
+    h->n_items += mmm_cells_energy_slots(h);
+  }
+  if (h->n_items == 0) h->n_items = 1;
+  if (h->n_planes > 0) {
+    const size_t cnt = (size_t)h->n_planes * 3 * (size_t)h->npad;
+    if ((rc = dev_alloc(h, &h->d_fpair, cnt))) return rc;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * cnt, h->stream));
   }
   if ((rc = dev_alloc(h, &h->d_epair, (size_t)h->n_items * 4))) return rc;
   MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
@@ -469,7 +478,9 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
   if ((rc = ensure_scratch(h))) return rc;
   if ((rc = mmm_launch_prepare(h, d_skip))) return rc;
   if (h->pair_mode == 3) {
-    if (h->pp.chb_form >= 0) {
+    if (h->pp.chb_form == MMM_CHB_POLYNOMIAL) {
+      if ((rc = mmm_launch_pair_n3(h, d_skip, true))) return rc;
+    } else if (h->pp.chb_form >= 0) {
       PairParams only_chb = h->pp;
       only_chb.ev_form = only_chb.cob_form = only_chb.scb_form = MMM_FORM_OFF;
       only_chb.cutoff2 = 0.0f;

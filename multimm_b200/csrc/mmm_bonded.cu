@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kAsmBlock) k_assemble(const AsmArgs A) {
       A.facc[i] = 0ull;
       A.facc[(size_t)A.npad + i] = 0ull;
       A.facc[2 * (size_t)A.npad + i] = 0ull;
-    } else if (A.fpair) {
+    }
+    if (A.fpair) {
       for (int c = 0; c < A.nchunk; ++c) {
         const double* fp = A.fpair + (size_t)c * 3 * (size_t)A.npad;
         fx += fp[i];
@@ -323,7 +324,7 @@ int mmm_launch_assemble(mmm_system* h, const int* d_skip) {
   AsmArgs A;
   A.x = h->d_x;
   A.fpair = (h->pair_mode == 1 || h->pair_mode == 3) ? h->d_fpair : nullptr;
-  A.facc = h->pair_mode == 2 ? h->d_facc : nullptr;
+  A.facc = (h->pair_mode == 2 || (h->pair_mode == 3 && h->n3_items > 0 && h->n3_chb_only)) ? h->d_facc : nullptr;
   A.nchunk = h->n_planes;
   A.n = h->n;
   A.npad = h->npad;

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) k_cell_ranges(const float4* __restrict__ 
 
 struct CellArgs {
   const float4* pos4s;
+  const uint32_t* keys;
   const int* order;
   const int* cstart;
   const int* cend;
@@ -133,7 +134,7 @@ struct CellArgs {
   double* fplane;   // [3][npad], indexed by ORIGINAL bead id
   double* epair;    // [n_cell_items][4]
   unsigned long long* npairs;  // [n_cell_items] ordered pairs inside the cut-off
-  int64_t npad;
+  int64_t n, npad;
   const int* skip;
   PairParams pp;    // CHB switched off (handled by the exact pass)
 };
@@ -144,55 +145,126 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+template <int P>
+__device__ __forceinline__ float powi(float w) {
+  if constexpr (P == 1) {
+    return w;
+  } else if constexpr (P % 2 == 0) {
+    const float hf = powi<P / 2>(w);
+    return hf * hf;
+  } else {
+    return w * powi<P - 1>(w);
+  }
+}
+
+// Default forms, specialised: power-law EV with integer power EVP, Gaussian SCB (GK & 1) / COB
+// (GK & 2).  ~30 instructions per candidate.  Forces in real units.
+template <int EVP, int GK>
+__device__ __forceinline__ bool pair_fast(const float4 pj, const IBead& b, const PairParams& c, bool live,
+                                          float& fx, float& fy, float& fz, float e4[4]) {
+  const float dx = b.x - pj.x, dy = b.y - pj.y, dz = b.z - pj.z;
+  float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  live = live && (r2 < c.cutoff2);
+  r2 = live ? r2 : 1.0f;
+  const float inv_r = fast_rsqrt(r2);
+  const float r = r2 * inv_r;
+  const float w = fast_rcp(r + c.ev_rs);
+  const float wp = live ? powi<EVP>(w) : 0.0f;
+  e4[0] += wp;  // x eps sigma^p at the end
+  float fs = ((float)EVP * c.ev_pref) * wp * w * inv_r;
+  if (GK != 0) {
+    const float g = live ? fast_ex2(r2 * c.g_c) : 0.0f;
+    const int xr = b.w ^ __float_as_int(pj.w);
+    if (GK & 1) {
+      const float g1 = ((xr & 0x7) == 0) ? g : 0.0f;
+      e4[2] += g1;  // x -eps_i at the end
+      fs = fmaf(-b.a_scb, g1, fs);
+    }
+    if (GK & 2) {
+      const float g2 = ((xr & 0x18) == 0) ? g : 0.0f;
+      e4[1] += g2;
+      fs = fmaf(-b.a_cob, g2, fs);
+    }
+  }
+  fx = fmaf(fs, dx, fx);
+  fy = fmaf(fs, dy, fy);
+  fz = fmaf(fs, dz, fz);
+  return live;
+}
+
+// One warp per 32 consecutive SORTED beads.  The beads of a warp lie in one or a few cells; the warp
+// takes its cells one at a time (lanes of other cells wait), so that all active lanes walk the same
+// j-list: the 27 neighbouring cells in fixed (z, y, x) order, broadcast loads.
+// EVP = 0: any functional form (pair_generic).
+template <int EVP, int GK>
 __global__ void __launch_bounds__(kCellWarps * 32) k_pair_cells(const CellArgs A) {
   __shared__ double s_red[5][kCellWarps];
   if (A.skip && *A.skip) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const CellGrid g = *A.grid;
   const PairParams& c = A.pp;
-  const uint32_t code = blockIdx.x * kCellWarps + warp;
+  const int64_t i = ((int64_t)blockIdx.x * kCellWarps + warp) * 32 + lane;
+  const bool valid = i < A.n;
   double de[4] = {0.0, 0.0, 0.0, 0.0};
+  double dfx = 0.0, dfy = 0.0, dfz = 0.0;
   unsigned long long cnt = 0;
-  int s0 = 0, s1 = 0;
-  if (code < (1u << (3 * g.bits))) { s0 = A.cstart[code]; s1 = A.cend[code]; }
-  if (s1 > s0) {
+  const float4 pi = A.pos4s[valid ? i : 0];
+  const int oi = A.order[valid ? i : 0];
+  const uint32_t mykey = A.keys[valid ? i : 0];
+  IBead b;
+  b.x = pi.x; b.y = pi.y; b.z = pi.z; b.w = __float_as_int(pi.w);
+  const int si = (b.w & 7) - 2;
+  float e_scb_i = 0.0f, e_cob_i = 0.0f;
+  if (c.scb_form >= 0 && si != 0) e_scb_i = c.scb_e[si == 2 ? 0 : (si == 1 ? 1 : (si == -1 ? 2 : 3))];
+  if (c.cob_form >= 0 && si != 0) e_cob_i = si > 0 ? c.cob_ea : c.cob_eb;
+  b.a_scb = e_scb_i * c.g_inv_rc2;
+  b.a_cob = e_cob_i * c.g_inv_rc2;
+
+  unsigned todo = __ballot_sync(0xffffffffu, valid);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const uint32_t code = __shfl_sync(0xffffffffu, mykey, leader);
+    const bool mine = valid && mykey == code;
+    todo &= ~__ballot_sync(0xffffffffu, mine);
     const int cx = (int)compact3(code), cy = (int)compact3(code >> 1), cz = (int)compact3(code >> 2);
-    for (int base = s0; base < s1; base += 32) {
-      const int i = base + lane;
-      const bool valid = i < s1;
-      const float4 pi = A.pos4s[valid ? i : s0];
-      const int oi = A.order[valid ? i : s0];
-      IBead b;
-      b.x = pi.x; b.y = pi.y; b.z = pi.z; b.w = __float_as_int(pi.w);
-      b.a_scb = 0.0f; b.a_cob = 0.0f;
-      const int si = (b.w & 7) - 2;
-      double dfx = 0.0, dfy = 0.0, dfz = 0.0;
-      for (int nz = cz - 1; nz <= cz + 1; ++nz) {
-        if (nz < 0 || nz >= g.dim) continue;
-        for (int ny = cy - 1; ny <= cy + 1; ++ny) {
-          if (ny < 0 || ny >= g.dim) continue;
-          for (int nx = cx - 1; nx <= cx + 1; ++nx) {
-            if (nx < 0 || nx >= g.dim) continue;
-            const uint32_t nc = spread3((uint32_t)nx) | (spread3((uint32_t)ny) << 1) | (spread3((uint32_t)nz) << 2);
-            const int j0 = A.cstart[nc], j1 = A.cend[nc];
-            float fx = 0.f, fy = 0.f, fz = 0.f, e4[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int j = j0; j < j1; ++j) {
-              const float4 pj = A.pos4s[j];
+    for (int nz = cz - 1; nz <= cz + 1; ++nz) {
+      if (nz < 0 || nz >= g.dim) continue;
+      for (int ny = cy - 1; ny <= cy + 1; ++ny) {
+        if (ny < 0 || ny >= g.dim) continue;
+        for (int nx = cx - 1; nx <= cx + 1; ++nx) {
+          if (nx < 0 || nx >= g.dim) continue;
+          const uint32_t nc = spread3((uint32_t)nx) | (spread3((uint32_t)ny) << 1) | (spread3((uint32_t)nz) << 2);
+          const int j0 = A.cstart[nc], j1 = A.cend[nc];
+          float fx = 0.f, fy = 0.f, fz = 0.f, e4[4] = {0.f, 0.f, 0.f, 0.f};
+          unsigned hits = 0;
+#pragma unroll 4
+          for (int j = j0; j < j1; ++j) {
+            const float4 pj = A.pos4s[j];
+            bool in;
+            if (EVP > 0) {
+              in = pair_fast<EVP, GK>(pj, b, c, mine && j != i, fx, fy, fz, e4);
+            } else {
               const int oj = A.order[j];
-              const bool in = pair_generic(pj, b, si, oi < oj, c, valid && j != i, fx, fy, fz, e4, c.cutoff2);
-              cnt += in ? 1ull : 0ull;
+              in = pair_generic(pj, b, si, oi < oj, c, mine && j != i, fx, fy, fz, e4, c.cutoff2);
             }
-            dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
-            de[0] += (double)e4[0]; de[1] += (double)e4[1]; de[2] += (double)e4[2]; de[3] += (double)e4[3];
+            hits += in ? 1u : 0u;
           }
+          cnt += hits;
+          dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
+          de[0] += (double)e4[0]; de[1] += (double)e4[1]; de[2] += (double)e4[2]; de[3] += (double)e4[3];
         }
       }
-      if (valid) {
-        A.fplane[oi] = dfx;
-        A.fplane[(size_t)A.npad + oi] = dfy;
-        A.fplane[2 * (size_t)A.npad + oi] = dfz;
-      }
     }
+  }
+  if (valid) {
+    A.fplane[oi] = dfx;
+    A.fplane[(size_t)A.npad + oi] = dfy;
+    A.fplane[2 * (size_t)A.npad + oi] = dfz;
+  }
+  if (EVP > 0) {
+    de[0] *= (double)c.ev_pref;
+    de[1] *= -(double)e_cob_i;
+    de[2] *= -(double)e_scb_i;
   }
   // each unordered pair was seen from both sides
   double v[5] = {0.5 * de[0], 0.5 * de[1], 0.5 * de[2], 0.5 * de[3], (double)cnt};
@@ -211,12 +283,19 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_pair_cells(const CellArgs A
   }
 }
 
+template <int EVP>
+void launch_cells_evp(const CellArgs& A, int gk, int blocks, cudaStream_t st) {
+  switch (gk) {
+    case 0: k_pair_cells<EVP, 0><<<blocks, kCellWarps * 32, 0, st>>>(A); break;
+    case 1: k_pair_cells<EVP, 1><<<blocks, kCellWarps * 32, 0, st>>>(A); break;
+    case 2: k_pair_cells<EVP, 2><<<blocks, kCellWarps * 32, 0, st>>>(A); break;
+    default: k_pair_cells<EVP, 3><<<blocks, kCellWarps * 32, 0, st>>>(A); break;
+  }
+}
+
 }  // namespace
 
-int64_t mmm_cells_energy_slots(const mmm_system* h) {
-  (void)h;
-  return kMaxCodes / kCellWarps;
-}
+int64_t mmm_cells_energy_slots(const mmm_system* h) { return (h->n + kCellWarps * 32 - 1) / (kCellWarps * 32); }
 
 int mmm_cells_alloc(mmm_system* h) {
   if (h->d_keys) return MMM_OK;
@@ -228,7 +307,7 @@ int mmm_cells_alloc(mmm_system* h) {
   MMM_CUDA(h, cudaMalloc((void**)&h->d_pos4_sorted, n * sizeof(float4)));
   MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_start, (size_t)2 * kMaxCodes * sizeof(int)));
   MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_grid, sizeof(CellGrid)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_npairs, (size_t)(kMaxCodes / kCellWarps) * sizeof(unsigned long long)));
+  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_npairs, (size_t)mmm_cells_energy_slots(h) * sizeof(unsigned long long)));
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->d_keys_tmp, h->d_keys, h->d_order_tmp, h->d_order, (int)n, 0, 30,
                                   h->stream);
@@ -264,6 +343,7 @@ int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
                                                d_skip);
   CellArgs A;
   A.pos4s = h->d_pos4_sorted;
+  A.keys = h->d_keys;
   A.order = h->d_order;
   A.cstart = cstart;
   A.cend = cend;
@@ -271,11 +351,19 @@ int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
   A.fplane = h->d_fpair + (size_t)h->cells_plane * 3 * (size_t)h->npad;
   A.epair = h->d_epair + (size_t)h->cells_item0 * 4;
   A.npairs = h->d_cell_npairs;
+  A.n = h->n;
   A.npad = h->npad;
   A.skip = d_skip;
   A.pp = h->pp;
   A.pp.chb_form = MMM_FORM_OFF;
-  k_pair_cells<<<kMaxCodes / kCellWarps, kCellWarps * 32, 0, h->stream>>>(A);
+  const int cblocks = (int)mmm_cells_energy_slots(h);
+  if (mmm_pair_fast_path_pp(A.pp) && A.pp.ev_form == MMM_EV_POWERLAW) {
+    const int gk = (A.pp.scb_form >= 0 ? 1 : 0) | (A.pp.cob_form >= 0 ? 2 : 0);
+    if (A.pp.ev_power == 6.0f) launch_cells_evp<6>(A, gk, cblocks, h->stream);
+    else launch_cells_evp<3>(A, gk, cblocks, h->stream);
+  } else {
+    k_pair_cells<0, 0><<<cblocks, kCellWarps * 32, 0, h->stream>>>(A);
+  }
   h->launches += 5;  // + the radix-sort kernels of CUB (library), not counted
   MMM_CUDA(h, cudaGetLastError());
   MMM_CUDA(h, cudaEventRecord(eb, h->stream));
@@ -303,7 +391,7 @@ int mmm_get_cell_grid(mmm_handle h, float* cell_out, int32_t* dim_out, float* or
     return mmm_fail(h, MMM_ERR_STATE, "mmm_get_cell_grid: no cut-off evaluation has run on this handle");
   cudaSetDevice(h->device);
   CellGrid g;
-  std::vector<unsigned long long> cnt((size_t)(kMaxCodes / kCellWarps));
+  std::vector<unsigned long long> cnt((size_t)mmm_cells_energy_slots(h));
   MMM_CUDA(h, cudaMemcpyAsync(&g, h->d_cell_grid, sizeof(g), cudaMemcpyDeviceToHost, h->stream));
   MMM_CUDA(h, cudaMemcpyAsync(cnt.data(), h->d_cell_npairs, cnt.size() * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, h->stream));

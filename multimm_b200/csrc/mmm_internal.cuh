@@ -153,7 +153,9 @@ struct mmm_system {
   int pair_kernel_pref = 0;      // 0 auto, 1 force the gather kernel (tests / A-B timing)
   unsigned long long* d_facc = nullptr;  // [3][npad] fixed-point force accumulator (Newton-3, cells)
   int2* d_items = nullptr;       // Newton-3 work items
-  int n3_cj = 1;                 // j-stages per item
+  int n3_items = 0;              // number of Newton-3 work items (their energy slots come first in d_epair)
+  bool n3_chb_only = false;      // the item list is the cut-off mode's CHB-only list
+  std::vector<int32_t> h_chrom;  // host copy of the chromosome ids (static; sizes the CHB-only item list)
 
   // reductions
   int n_red_blocks = 0;
@@ -214,8 +216,8 @@ bool mmm_pair_fast_path(const mmm_system* h);
 bool mmm_pair_fast_path_pp(const PairParams& p);
 // mmm_pair_n3.cu
 bool mmm_pair_n3_eligible(const mmm_system* h);
-int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, int* cj_out);
-int mmm_launch_pair_n3(mmm_system* h, const int* d_skip);  // d_pos4 -> d_facc, d_epair
+int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, bool chb_only);
+int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only = false);  // d_pos4 -> d_facc, d_epair
 // mmm_cells.cu
 int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip);
 int64_t mmm_cells_energy_slots(const mmm_system* h);

@@ -35,6 +35,8 @@
 // unordered pair: 3 FADD, FMUL + 2 FFMA (r^2), MUFU.SQRT, FFMA (q = r^2 + r_s r), MUFU.RCP
 // (w/r), FMUL (w), 3 FMUL (w^6), FADD (energy), FMUL, 6 FFMA (both force accumulators).
 // Roofline: instruction issue (128 lanes/clk/SM); MUFU.SQRT/RCP co-issue (measured 32 lanes/clk/SM).
+#include <algorithm>
+
 #include "mmm_internal.cuh"
 
 namespace {
@@ -93,11 +95,11 @@ struct N3Args {
   const TileInfo* tiles;
   unsigned long long* facc;  // [3][npad] fixed-point force, units 2^-24 kJ/mol/nm
   double* epair;             // [n_items][4]
-  const int2* items;         // (i-block, first j-stage)
+  const int2* items;         // (i-block, first j-stage | number of stages << 24)
   int* counter;
   const int* skip;
   int64_t npad;
-  int n_items, n_jstages, cj;
+  int n_items;
   double fscale;             // U * 2^24
   double e_ev, e_gauss, e_chb;  // energy prefactors: eps sigma^p; -rc^2 U; dE
   N3Consts c;
@@ -144,13 +146,16 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
         r2 = self ? 1.0f : r2;
       }
       const float r = fast_sqrt(r2);
-      const float q = fmaf(c.ev_rs, r, r2);
-      const float wr = fast_rcp(q);  // w / r with w = 1 / (r + r_s)
-      const float w = r * wr;
-      float wp = powi<EVP>(w);
-      if (SELF) wp = self ? 0.0f : wp;
-      E.ev += wp;
-      float fs = wp * wr;  // -(dE_ev/dr) / r in units of U
+      float fs = 0.0f;
+      if constexpr (EVP > 0) {
+        const float q = fmaf(c.ev_rs, r, r2);
+        const float wr = fast_rcp(q);  // w / r with w = 1 / (r + r_s)
+        const float w = r * wr;
+        float wp = powi<EVP>(w);
+        if (SELF) wp = self ? 0.0f : wp;
+        E.ev += wp;
+        fs = wp * wr;  // -(dE_ev/dr) / r in units of U
+      }
       if (kTypes) {
         const int ti = __float_as_int(si4[ii].w);
         const int xr = ti ^ tj;
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
     const int item = s_item;
     if (item >= A.n_items) break;
     const int2 it = A.items[item];
-    const int iblk = it.x, js0 = it.y, js1 = min(js0 + A.cj, A.n_jstages);
+    const int iblk = it.x, js0 = it.y & 0xFFFFFF, js1 = js0 + (it.y >> 24);
     const int64_t ibase = (int64_t)iblk * N3_IB;
     const int iw = warp * 64 + a * 8;  // first of this lane's i-beads within the block
 
@@ -359,6 +364,7 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
             const float ddz = fmaxf(0.0f, fmaxf(ib.loz - jt.hiz, jt.loz - ib.hiz));
             near = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) < c.rg2;
           }
+          if (EVP == 0 && chb_mode == 0) continue;  // CHB-only pass: nothing to do for this tile pair
           if (near) {
             step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
           } else if (!CHB || chb_mode == 0) {
@@ -477,24 +483,49 @@ bool mmm_pair_n3_eligible(const mmm_system* h) {
   return true;
 }
 
-int64_t mmm_n3_jstages(const mmm_system* h) { return h->npad / N3_JB; }
-
-// Work items: for every i-block, runs of cj j-stages starting at the diagonal.
-int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, int* cj_out) {
+// Work items: for every i-block, runs of at most cj j-stages starting at the diagonal.
+// chb_only (cut-off mode's exact CHB pass): only stages whose chromosome range overlaps the
+// i-block's are visited; chromosome ids are static, so the list is built once on the host.
+int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, bool chb_only) {
   const int64_t nib = h->npad / N3_IB, njs = h->npad / N3_JB;
+  // chromosome range of every j-stage (real beads only)
+  std::vector<int> lo((size_t)njs, 0x7fffffff), hi((size_t)njs, -1);
+  if (chb_only) {
+    for (int64_t i = 0; i < h->n; ++i) {
+      const int c = h->h_chrom.empty() ? 0 : h->h_chrom[(size_t)i];
+      const int64_t s = i / N3_JB;
+      lo[s] = std::min(lo[s], c);
+      hi[s] = std::max(hi[s], c);
+    }
+  }
+  auto wanted = [&](int64_t ib, int64_t js) {
+    if (!chb_only) return true;
+    if ((js >> 1) == ib) return hi[js] >= 0;  // diagonal stages (unless padding only)
+    const int ilo = std::min(lo[2 * ib], lo[2 * ib + 1]), ihi = std::max(hi[2 * ib], hi[2 * ib + 1]);
+    return hi[js] >= 0 && ihi >= 0 && !(ihi < lo[js] || hi[js] < ilo);
+  };
   int64_t pairs = 0;
-  for (int64_t i = 0; i < nib; ++i) pairs += njs - 2 * i;
+  for (int64_t i = 0; i < nib; ++i)
+    for (int64_t js = 2 * i; js < njs; ++js) pairs += wanted(i, js) ? 1 : 0;
   const int64_t target_items = (int64_t)h->sm_count * 2 * 48;
   int64_t cj = pairs / target_items;
   cj = cj < 1 ? 1 : (cj > 16 ? 16 : cj);
   items.clear();
-  for (int64_t i = 0; i < nib; ++i)
-    for (int64_t js = 2 * i; js < njs; js += cj) items.push_back(make_int2((int)i, (int)js));
-  *cj_out = (int)cj;
+  for (int64_t i = 0; i < nib; ++i) {
+    int64_t js = 2 * i;
+    while (js < njs) {
+      if (!wanted(i, js)) { ++js; continue; }
+      int64_t cnt = 1;
+      while (cnt < cj && js + cnt < njs && wanted(i, js + cnt)) ++cnt;
+      items.push_back(make_int2((int)i, (int)(js | (cnt << 24))));
+      js += cnt;
+    }
+  }
+  if (items.empty()) items.push_back(make_int2(0, 0));  // zero stages: the kernel writes a zero energy slot
   return MMM_OK;
 }
 
-int mmm_launch_pair_n3(mmm_system* h, const int* d_skip) {
+int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   const PairParams& p = h->pp;
   N3Args A;
   A.pos4 = h->d_pos4;
@@ -505,20 +536,19 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip) {
   A.counter = h->d_counter;
   A.skip = d_skip;
   A.npad = h->npad;
-  A.n_items = (int)h->n_items;
-  A.n_jstages = (int)(h->npad / N3_JB);
-  A.cj = h->n3_cj;
-  // U = p eps sigma^p in double, from the float parameters the gather kernel uses too
-  const double U = (double)p.ev_power * (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
+  A.n_items = h->n3_items;
+  // U = p eps sigma^p in double, from the float parameters the gather kernel uses too (1 in the
+  // CHB-only pass, where EV is not evaluated)
+  const double U = chb_only ? 1.0 : (double)p.ev_power * (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
   A.fscale = U * N3_FIXED;
-  A.e_ev = (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
+  A.e_ev = chb_only ? 0.0 : (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
   N3Consts& c = A.c;
   c.ev_rs = p.ev_rs;
   c.g_c = p.g_c;
   c.rg2 = p.rg2;
   c.chb_kc = p.chb_kc;
   c.chb_c = p.chb_form >= 0 ? (float)((double)p.chb_de / U) : 0.0f;
-  c.gk = (p.scb_form >= 0 ? 1 : 0) | (p.cob_form >= 0 ? 2 : 0);
+  c.gk = chb_only ? 0 : ((p.scb_form >= 0 ? 1 : 0) | (p.cob_form >= 0 ? 2 : 0));
   const double rc = p.scb_form >= 0 ? p.scb_rc : p.cob_rc;
   const double inv = rc > 0.0 ? 1.0 / (rc * rc * U) : 0.0;
   // s + 2 = 0..4 <-> s = -2..2 ; scb_e = {Ea1 (s=2), Ea2 (s=1), Eb1 (s=-1), Eb2 (s=-2)}
@@ -535,16 +565,18 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip) {
   A.e_chb = (double)p.chb_de;
 
   MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
-  const bool collect = h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
+  const bool timed = !chb_only;  // the CHB-only pass is timed with the cell-list pass
+  const bool collect = timed && h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
   cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
   cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
   if (collect) h->ev_cursor++;
-  MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+  if (timed) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
   const bool chb = p.chb_form >= 0;
-  if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
+  if (chb_only) launch_n3<0, 0, true>(h, A);
+  else if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
   else launch_n3_evp<3>(h, A, c.gk, chb);
   h->launches++;
   MMM_CUDA(h, cudaGetLastError());
-  MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  if (timed) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
 }
