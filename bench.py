@@ -215,6 +215,27 @@ def pair_flops(m) -> tuple[float, float]:
     return flops, pairs
 
 
+def max_over_ranks(values, device):
+    """Device timings are reduced with MAX over ranks (no-op for one process)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def whole_job_rate(world: int, steps: int, total_ms: float) -> float:
+    """Evaluations of all ranks per second of the slowest rank (weak scaling: one replica per GPU)."""
+    return world * steps / (total_ms * 1e-3)
+
+
+def replica_seed(rank: int) -> int:
+    """Rank r runs ensemble member r (SHUFFLING_SEED = r, run.py:473-476)."""
+    return rank
+
+
 def run_ours(opt):
     import torch
     import torch.distributed as dist
@@ -233,7 +254,7 @@ def run_ours(opt):
 
     with tempfile.TemporaryDirectory(prefix="mmm_bench_") as tmp:
         t_build0 = time.perf_counter()
-        m = build_model(opt.workload, seed=rank, device=local, tmp=tmp)
+        m = build_model(opt.workload, seed=replica_seed(rank), device=local, tmp=tmp)
         eng = m.engine
         build_s = time.perf_counter() - t_build0
         n = m.args.N_BEADS
@@ -251,11 +272,8 @@ def run_ours(opt):
             total_ms, pair_ms = eng.evaluate_timed(K, flush_l2=True)
             barrier()
         launches = eng.launch_count - launches0
-        t = torch.tensor([total_ms, pair_ms], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, pair_ms_max = float(t[0]), float(t[1])
-        value = world * K / (total_ms * 1e-3)
+        total_ms, pair_ms_max = max_over_ranks([total_ms, pair_ms], device=f"cuda:{local}")
+        value = whole_job_rate(world, K, total_ms)
 
         # ---- end to end through the C-ABI with host buffers ------------------------------------
         x_host = torch.from_numpy(m.positions.copy()).pin_memory()
@@ -270,10 +288,7 @@ def run_ours(opt):
             e_terms, forces = eng.energy_forces()
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * K / float(t[0])
+        e2e_value = whole_job_rate(world, K, 1e3 * max_over_ranks([e2e_s], device=f"cuda:{local}")[0])
 
         if rank != 0:
             m.close()

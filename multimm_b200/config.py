@@ -18,7 +18,7 @@ import os
 from enum import Enum
 from typing import Any, Optional
 
-from pydantic import BaseModel, BeforeValidator, create_model, model_validator
+from pydantic import BaseModel, BeforeValidator, WithJsonSchema, create_model, model_validator
 from typing_extensions import Annotated
 
 from .units import Quantity, parse_quantity
@@ -71,7 +71,8 @@ def _to_chrom(v: Any) -> Optional[str]:
     return text if text.startswith("chr") else f"chr{text}"
 
 
-Q = Annotated[Quantity, BeforeValidator(_to_quantity)]
+Q = Annotated[Quantity, BeforeValidator(_to_quantity),
+              WithJsonSchema({"type": "string", "description": "'<float> <unit expression>', e.g. '0.1 nanometer'"})]
 B = Annotated[bool, BeforeValidator(_to_bool)]
 Chrom = Annotated[Optional[str], BeforeValidator(_to_chrom)]
 

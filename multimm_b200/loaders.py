@@ -168,6 +168,9 @@ def import_mns_from_bedpe(bedpe_file, N_beads, coords=None, chrom=None, threshol
     ns[ns >= N_beads] = N_beads - 1
     sel = ns > ms + min_loop_dist
     ms, ns, cs = ms[sel], ns[sel], cs[sel]
+    if cs.size == 0:  # the reference fails with an IndexError on cs[0] here (utils.py:520); say why instead
+        raise ValueError("No loop spans more than min_loop_dist beads at this resolution. Please increase N_BEADS "
+                         "or model a shorter region.")
     ds = 0.1 + 0.1 * _minmax_raw(1 / cs ** (2 / 3)) if not np.all(cs == cs[0]) else np.ones(len(ms))
     if down_prob < 1.0:
         pick = np.where(np.random.rand(len(ms)) < down_prob)[0]

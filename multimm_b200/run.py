@@ -1,0 +1,352 @@
+"""Command line and ensemble driver — mirror of the reference's ``run.py``
+(src/multimm/run.py:60-500) on the minimisation path.
+
+    python -m multimm_b200.run -c config.ini [--field value ...] [--gpus 0,1,...]
+
+Same precedence (defaults < ini < CLI, run.py:367-382), same MODELLING_LEVEL presets
+(run.py:128-213), same cross-field checks (run.py:219-331), same ``metadata/config_auto.ini`` /
+``metadata/output.log`` side products, same ensemble semantics (run.py:471-485: replica i runs
+with SHUFFLING_SEED = i in ``run_<i>``, is archived to ``run_<i>.tar.gz`` and its directory
+removed).  What changes: ensemble members are independent, so they are dealt to the visible
+B200s, one worker process per GPU, replica i -> GPU i mod G, with no communication between
+workers (the reference runs them one after the other in a single Python loop).
+"""
+from __future__ import annotations
+
+import argparse
+import configparser
+import logging
+import multiprocessing as mp
+import os
+import shutil
+import sys
+import tarfile
+import time
+from enum import Enum
+
+from . import loaders
+from .config import SimulationConfig
+from .units import Quantity
+
+logger = logging.getLogger("multimm_b200")
+
+
+class Tee:
+    """run.py:60-71"""
+
+    def __init__(self, *streams):
+        self.streams = streams
+
+    def write(self, data):
+        for s in self.streams:
+            s.write(data)
+            s.flush()
+
+    def flush(self):
+        for s in self.streams:
+            s.flush()
+
+
+# MODELLING_LEVEL presets (run.py:137-213).  `None` = "on iff a compartment file was given".
+_OFF5 = dict(SC_USE_SPHERICAL_CONTAINER=False, CHB_USE_CHROMOSOMAL_BLOCKS=False, SCB_USE_SUBCOMPARTMENT_BLOCKS=False,
+             IBL_USE_B_LAMINA_INTERACTION=False, CF_USE_CENTRAL_FORCE=False)
+PRESETS = {
+    "gene": dict(N_BEADS=1000, **_OFF5, COB_USE_COMPARTMENT_BLOCKS=False, SHUFFLE_CHROMS=False, SIM_RUN_MD=True,
+                 SIM_N_STEPS=10000),
+    "region": dict(N_BEADS=5000, **_OFF5, COB_USE_COMPARTMENT_BLOCKS=None, SIM_RUN_MD=True, SIM_N_STEPS=10000),
+    "chromosome": dict(N_BEADS=20000, **_OFF5, COB_USE_COMPARTMENT_BLOCKS=None, SIM_RUN_MD=True, SIM_N_STEPS=10000),
+    "gw": dict(N_BEADS=200000, SC_USE_SPHERICAL_CONTAINER=True, CHB_USE_CHROMOSOMAL_BLOCKS=False,
+               SCB_USE_SUBCOMPARTMENT_BLOCKS=False, COB_USE_COMPARTMENT_BLOCKS=None, IBL_USE_B_LAMINA_INTERACTION=None,
+               CF_USE_CENTRAL_FORCE=False, SIM_RUN_MD=False, SIM_N_STEPS=10000),
+}
+_ALIASES = {"loc": "region", "chrom": "chromosome", "genome": "gw"}
+
+
+class ArgumentChanger:
+    """run.py:73-217: presets that silently override flags; every change is reported."""
+
+    def __init__(self, args, chrom_sizes=None):
+        self.args = args
+        self.chrom_sizes = chrom_sizes or loaders.CHROM_SIZES
+        self.changed: dict = {}
+
+    def set_arg(self, name, value):
+        if not hasattr(self.args, name):
+            logger.warning(f"Argument '{name}' not found in args object.")
+            return
+        self.changed.setdefault(name, getattr(self.args, name))
+        setattr(self.args, name, value)
+
+    def convenient_argument_changer(self):
+        # nucleosome interpolation is always forced off (run.py:130-131)
+        self.set_arg("NUC_DO_INTERPOLATION", False)
+        self.set_arg("ATACSEQ_PATH", None)
+        level = str(self.args.MODELLING_LEVEL or "").lower()
+        level = _ALIASES.get(level, level)
+        preset = PRESETS.get(level)
+        if preset:
+            logger.warning(f"{level}-level modelling activated. This will overwrite parameters.")
+            has_comps = bool(self.args.COMPARTMENT_PATH)
+            for name, value in preset.items():
+                self.set_arg(name, has_comps if value is None else value)
+            if level == "chromosome":
+                self.set_arg("LOC_START", 1)
+                self.set_arg("LOC_END", self.chrom_sizes[self.args.CHROM])
+            self.report()
+
+    def report(self):
+        rows = [(k, old, getattr(self.args, k)) for k, old in self.changed.items() if old != getattr(self.args, k)]
+        if rows:
+            logger.warning("MODELLING LEVEL OVERRIDE ACTIVE: parameters have been overwritten.")
+            print("\nChanged parameters:\n" + "-" * 60)
+            for k, old, new in rows:
+                print(f"{k:35s} : {old}  ->  {new}")
+            print("-" * 60 + "\n")
+
+
+def _empty(v) -> bool:
+    return v is None or v == ""
+
+
+def args_tests(args):
+    """Cross-field validation, run.py:219-331: same conditions, same order, same exception type."""
+
+    def check_file(path, name, hint):
+        if not _empty(path) and not os.path.exists(path):
+            raise ValueError(f"{name} file was provided but not found: {path} (expected {hint})")
+
+    if _empty(args.LOOPS_PATH):
+        raise ValueError("Loops interaction data is required to run MultiMM. "
+                         "Please provide a valid .bedpe file via LOOPS_PATH.")
+    check_file(args.LOOPS_PATH, "Loops (.bedpe)", ".bedpe")
+    check_file(args.COMPARTMENT_PATH, "Compartment data", ".bed")
+    check_file(args.ATACSEQ_PATH, "Nucleosome/ATAC data", ".bigwig")
+
+    no_comps = _empty(args.COMPARTMENT_PATH)
+    if no_comps and args.COB_USE_COMPARTMENT_BLOCKS:
+        raise ValueError("Compartment modeling is enabled, but no compartment data was provided. "
+                         "Please supply a .bed file or disable COB_USE_COMPARTMENT_BLOCKS.")
+    elif args.NUC_DO_INTERPOLATION and args.ATACSEQ_PATH is None:
+        raise ValueError("Nucleosome interpolation is enabled, but no occupancy data was found. "
+                         "Provide a .bigwig file via ATACSEQ_PATH or disable NUC_DO_INTERPOLATION.")
+    elif no_comps and args.SCB_USE_SUBCOMPARTMENT_BLOCKS:
+        raise ValueError("Subcompartment modeling requires input data. "
+                         "Please provide a .bed file or disable SCB_USE_SUBCOMPARTMENT_BLOCKS.")
+    elif args.COMPARTMENT_PATH is None and args.IBL_USE_B_LAMINA_INTERACTION:
+        raise ValueError("Lamina interactions depend on compartment annotations. "
+                         "Please provide a compartment .bed file or disable IBL_USE_B_LAMINA_INTERACTION.")
+    elif args.IBL_USE_B_LAMINA_INTERACTION and not (args.SCB_USE_SUBCOMPARTMENT_BLOCKS or args.COB_USE_COMPARTMENT_BLOCKS):
+        raise ValueError("Lamina interactions are enabled but no compartment-based forces are active. Enable "
+                         "COB_USE_COMPARTMENT_BLOCKS or SCB_USE_SUBCOMPARTMENT_BLOCKS, or disable lamina interactions.")
+    elif args.CF_USE_CENTRAL_FORCE and args.CHROM is not None:
+        raise ValueError("Central force attraction to the nucleolus is typically used for whole-genome simulations. "
+                         "Since you are modeling a single chromosome or region, consider disabling CF_USE_CENTRAL_FORCE.")
+    elif args.CHB_USE_CHROMOSOMAL_BLOCKS and args.CHROM is not None:
+        # the reference only warns here (run.py:296-300), although its own test expects a raise
+        logger.warning("Chromosomal block interactions are more meaningful in multi-chromosome systems. "
+                       "You may want to disable CHB_USE_CHROMOSOMAL_BLOCKS for single-chromosome simulations.")
+
+    single = args.CHROM is not None and args.CHROM != ""
+    if args.SHUFFLE_CHROMS and single:
+        logger.warning("Chromosome shuffling is enabled, but you are simulating a specific chromosomal region.")
+    if single and args.IBL_USE_B_LAMINA_INTERACTION:
+        logger.warning("Lamina interactions are enabled; they are typically more relevant in whole-genome simulations.")
+    if single and args.SC_USE_SPHERICAL_CONTAINER:
+        logger.warning("A spherical container is being used; it is generally more meaningful for the full genome.")
+    if not (args.POL_USE_HARMONIC_BOND and args.POL_USE_HARMONIC_ANGLE and args.EV_USE_EXCLUDED_VOLUME):
+        logger.warning("Some fundamental backbone forces are disabled. Make sure this is intentional.")
+    if args.CHB_USE_CHROMOSOMAL_BLOCKS:
+        logger.warning("Chromosomal block forces are enabled. These are approximate.")
+
+
+def read_ini(path: str) -> dict:
+    """Flat {UPPER_NAME: value} over all sections, DEFAULT last (run.py:334-346, 372-377)."""
+    cp = configparser.ConfigParser()
+    cp.read(path)
+    raw: dict = {}
+    for section in cp.sections():
+        for name, value in dict(cp[section]).items():
+            raw[name.upper()] = value
+    for name, value in dict(cp.defaults()).items():
+        raw[name.upper()] = value
+    return raw
+
+
+def get_config(argv=None):
+    """defaults < ini < CLI, then the MODELLING_LEVEL presets, then config_auto.ini (run.py:349-395)."""
+    ap = argparse.ArgumentParser(prog="multimm_b200")
+    ap.add_argument("-c", "--config_file", metavar="FILE", help="config file (ini format)")
+    ap.add_argument("--gpus", default=None, help="comma-separated CUDA device indices for ensemble workers "
+                                                 "(default: DEVICE, or every visible GPU for ensembles)")
+    for name in SimulationConfig.model_fields:
+        ap.add_argument(f"--{name.lower()}")
+    ns = vars(ap.parse_args(argv))
+    raw = read_ini(ns["config_file"]) if ns.get("config_file") else {}
+    for name, value in ns.items():
+        if name not in ("config_file", "gpus") and value is not None:
+            raw[name.upper()] = value
+    try:
+        args = SimulationConfig(**raw)
+    except Exception as e:
+        logger.error(f"Configuration validation failed: {e}")
+        raise
+    ArgumentChanger(args).convenient_argument_changer()
+    write_config(args)
+    return args, ns.get("gpus")
+
+
+def write_config(args) -> str:
+    """metadata/config_auto.ini (run.py:398-420)."""
+    meta = os.path.join(args.OUT_PATH, "metadata")
+    os.makedirs(meta, exist_ok=True)
+    path = os.path.join(meta, "config_auto.ini")
+    cp = configparser.ConfigParser()
+    cp["DEFAULT"] = {}
+    for name, value in args.model_dump().items():
+        if isinstance(value, Quantity):
+            cp["DEFAULT"][name] = f"{value._value} {value.unit.get_name()}"
+        elif isinstance(value, Enum):
+            cp["DEFAULT"][name] = value.value
+        elif value is None:
+            cp["DEFAULT"][name] = ""
+        else:
+            cp["DEFAULT"][name] = str(value)
+    with open(path, "w") as fh:
+        cp.write(fh)
+    logger.info(f"Configuration saved to {path}")
+    return path
+
+
+def archive_run(run_path: str) -> str:
+    """tar.gz the run directory, delete it only if the archive exists and is non-empty (run.py:423-445)."""
+    tar_path = run_path + ".tar.gz"
+    with tarfile.open(tar_path, "w:gz") as tar:
+        tar.add(run_path, arcname=os.path.basename(run_path))
+    if os.path.exists(tar_path) and os.path.getsize(tar_path) > 0:
+        shutil.rmtree(run_path)
+    else:
+        raise RuntimeError(f"Archive creation failed ({tar_path}). Original directory was NOT deleted.")
+    return tar_path
+
+
+# ---------------------------------------------------------------------------------------------
+# ensemble: replicas dealt to GPUs, one worker process per GPU, no communication
+# ---------------------------------------------------------------------------------------------
+def replica_paths(out_path: str, n_ensemble: int) -> list[str]:
+    width = len(str(max(n_ensemble - 1, 0)))
+    return [os.path.join(out_path, f"run_{i:0{width}d}") for i in range(n_ensemble)]
+
+
+def assign_replicas(n_ensemble: int, devices: list[int]) -> dict[int, list[int]]:
+    """Replica i -> devices[i mod G]."""
+    plan: dict[int, list[int]] = {d: [] for d in devices}
+    for i in range(n_ensemble):
+        plan[devices[i % len(devices)]].append(i)
+    return plan
+
+
+def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool = True) -> dict:
+    """One ensemble member: SHUFFLING_SEED = i, OUT_PATH = run_<i> (run.py:473-485)."""
+    from .model import MultiMM
+
+    cfg = SimulationConfig(**{**params, "SHUFFLING_SEED": i, "OUT_PATH": run_path})
+    os.makedirs(run_path, exist_ok=True)
+    t0 = time.time()
+    md = MultiMM(cfg, device=device)
+    try:
+        rep = md.run()
+    finally:
+        md.close()
+    out = dict(replica=i, device=device, seconds=time.time() - t0, **(rep or {}), **md.timings)
+    if archive:
+        out["archive"] = archive_run(run_path)
+    return out
+
+
+def _worker(params: dict, paths: list[str], todo: list[int], device: int, archive: bool, queue):
+    for i in todo:
+        try:
+            queue.put(("ok", run_replica(params, i, paths[i], device, archive)))
+        except Exception as e:  # report and keep going with the next replica
+            queue.put(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
+
+
+def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -> list[dict]:
+    """All N_ENSEMBLE members; returns one report per replica, ordered by replica index."""
+    n = int(args.N_ENSEMBLE or 0)
+    if n <= 0:
+        raise ValueError("GENERATE_ENSEMBLE is set but N_ENSEMBLE is not a positive integer")
+    if not devices:
+        devices = visible_devices(args)
+    params = {k: v for k, v in args.model_dump().items()}
+    paths = replica_paths(args.OUT_PATH, n)
+    plan = assign_replicas(n, devices)
+    if len(devices) == 1:
+        return [run_replica(params, i, paths[i], devices[0], archive) for i in range(n)]
+    ctx = mp.get_context("spawn")  # CUDA contexts must not be forked
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(params, paths, todo, dev, archive, queue))
+             for dev, todo in plan.items() if todo]
+    for p in procs:
+        p.start()
+    results, errors = [], []
+    for _ in range(n):
+        kind, payload = queue.get()
+        (results if kind == "ok" else errors).append(payload)
+    for p in procs:
+        p.join()
+    if errors:
+        raise RuntimeError(f"{len(errors)} ensemble member(s) failed: {errors}")
+    return sorted(results, key=lambda r: r["replica"])
+
+
+def visible_devices(args) -> list[int]:
+    dev = str(getattr(args, "DEVICE", "") or "").strip()
+    if dev.isdigit():
+        return [int(dev)]
+    if args.GENERATE_ENSEMBLE:
+        try:
+            import torch
+
+            n = torch.cuda.device_count()
+        except Exception:
+            n = 0
+        return list(range(n)) if n > 0 else [0]
+    return [0]
+
+
+def main(argv=None) -> int:
+    try:
+        args, gpus = get_config(argv)
+        args_tests(args)
+        log_dir = os.path.join(args.OUT_PATH, "metadata")
+        os.makedirs(log_dir, exist_ok=True)
+        with open(os.path.join(log_dir, "output.log"), "w") as log_file:
+            out, err = sys.stdout, sys.stderr
+            sys.stdout, sys.stderr = Tee(out, log_file), Tee(err, log_file)
+            try:
+                devices = [int(t) for t in gpus.split(",")] if gpus else visible_devices(args)
+                if args.GENERATE_ENSEMBLE:
+                    t0 = time.time()
+                    reports = run_ensemble(args, devices)
+                    dt = time.time() - t0
+                    print(f"ensemble of {len(reports)} structures on {len(devices)} GPU(s) in {dt:.1f} s "
+                          f"({3600.0 * len(reports) / dt:.1f} structures/hour)")
+                else:
+                    from .model import MultiMM
+
+                    md = MultiMM(args, device=devices[0])
+                    try:
+                        md.run()
+                    finally:
+                        md.close()
+            finally:
+                sys.stdout, sys.stderr = out, err
+        return 0
+    except Exception as e:
+        logger.error(f"ERROR: {e}")
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

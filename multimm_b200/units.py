@@ -65,6 +65,11 @@ UNITS = {
     "kilojoule_per_mole": _u(1.0, "kilojoule/mole", E=1), "kilojoules_per_mole": _u(1.0, "kilojoule/mole", E=1),
     "kilocalorie_per_mole": _u(_KCAL, "kilocalorie/mole", E=1),
     "kilocalories_per_mole": _u(_KCAL, "kilocalorie/mole", E=1),
+    # the names get_name() writes into config_auto.ini ("kilojoule/mole/nanometer**2") must parse
+    # back: energy per amount x amount, so that kilojoule/mole == kilojoule_per_mole
+    "kilojoule": _u(1.0, "kilojoule", E=1, N=1), "kilojoules": _u(1.0, "kilojoule", E=1, N=1),
+    "kilocalorie": _u(_KCAL, "kilocalorie", E=1, N=1), "kilocalories": _u(_KCAL, "kilocalorie", E=1, N=1),
+    "mole": _u(1.0, "mole", N=1), "moles": _u(1.0, "mole", N=1),
     # angle (-> rad)
     "radian": _u(1.0, "radian", A=1), "radians": _u(1.0, "radian", A=1),
     "degree": _u(math.pi / 180.0, "degree", A=1), "degrees": _u(math.pi / 180.0, "degree", A=1),
