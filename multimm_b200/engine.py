@@ -139,10 +139,13 @@ class Engine:
         return out
 
     # -- evaluation -------------------------------------------------------------------------
-    def energy_forces(self, want_forces: bool = True):
-        """Per-term energies (10,) kJ/mol and forces (N,3) kJ/mol/nm at the current positions."""
+    def energy_forces(self, want_forces: bool = True, out=None):
+        """Per-term energies (10,) kJ/mol and forces (N,3) kJ/mol/nm at the current positions.
+        ``out``: optional preallocated C-contiguous float64 (N,3) array for the forces (e.g. pinned)."""
         e = np.zeros(NUM_TERMS)
-        f = np.empty((self.n, 3)) if want_forces else None
+        if out is not None and (out.shape != (self.n, 3) or out.dtype != np.float64 or not out.flags.c_contiguous):
+            raise ValueError("out must be a C-contiguous float64 (N, 3) array")
+        f = (out if out is not None else np.empty((self.n, 3))) if want_forces else None
         self._ck(self._lib.mmm_energy_forces(self._h, _p(e), _p(f)))
         return e, f
 
