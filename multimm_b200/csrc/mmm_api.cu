@@ -95,6 +95,7 @@ int mmm_create(int device, int64_t n_beads, mmm_handle* out) {
   if ((rc = dev_alloc(h, &h->d_x, n3))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_center, 3))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_pos4, (size_t)h->npad))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->d_soa, 3 * (size_t)h->npad))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_tiles, (size_t)h->ntiles))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_g, n3))) return fail(rc);
   if ((rc = dev_alloc(h, &h->d_counter, 4))) return fail(rc);
@@ -123,7 +124,7 @@ int mmm_destroy(mmm_handle h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_type, h->d_cstr, h->d_s, h->d_bl_ptr, h->d_bl_partner, h->d_bl_flags, h->d_bl_r0, h->d_bl_k,
-                  h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_tiles, h->d_g,
+                  h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_soa, h->d_tiles, h->d_g,
                   h->d_fpair, h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
                   h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs};

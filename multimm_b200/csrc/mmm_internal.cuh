@@ -135,6 +135,7 @@ struct mmm_system {
   double* d_x = nullptr;         // [3n] master positions (nm), row-major N x 3
   double* d_center = nullptr;    // [3] centre used for the FP32 copy
   float4* d_pos4 = nullptr;      // [npad] centred FP32 xyz + type bits
+  float* d_soa = nullptr;        // [3][npad] the same coordinates as planes
   TileInfo* d_tiles = nullptr;   // [ntiles]
   double* d_g = nullptr;         // [3n] gradient (= -force)
 

@@ -47,6 +47,9 @@ constexpr int N3_IB = 512;                 // i-beads per block
 constexpr int N3_JB = 256;                 // j-beads per stage
 constexpr int N3_STEPS = N3_JB / MMM_TILE; // 8
 constexpr double N3_FIXED = 16777216.0;    // 2^24
+#ifndef N3_USE_F32X2
+#define N3_USE_F32X2 1
+#endif
 
 static_assert(N3_IB == MMM_PAD_TO, "npad must be a multiple of the i-block");
 static_assert(N3_IB == N3_WARPS * 64, "a warp owns 64 i-beads");
@@ -92,6 +95,7 @@ struct N3Consts {
 
 struct N3Args {
   const float4* pos4;
+  const float* soa;          // [3][npad] coordinate planes
   const TileInfo* tiles;
   unsigned long long* facc;  // [3][npad] fixed-point force, units 2^-24 kJ/mol/nm
   double* epair;             // [n_items][4]
@@ -105,14 +109,124 @@ struct N3Args {
   N3Consts c;
 };
 
+
+typedef unsigned long long u64;
+
+// Packed FP32 pairs (sm_100 f32x2 arithmetic: FFMA2 / FMUL2 / FADD2).  One issue slot does two
+// FP32 operations, so the hot loop is bound by the FMA pipe (19 lane-ops per pair) instead of
+// by instruction issue (21 per pair); MUFU works on the halves of a pair in place, ptxas
+// coalesces the pack/unpack moves away.
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// Positions live as packed register pairs (beads 2m, 2m+1) so that the f32x2 path reads them
+// without moves; the scalar variants address the halves.
 struct IBeads {
-  float x[8], y[8], z[8];
+  u64 x2[4], y2[4], z2[4];
   float fx[8], fy[8], fz[8];
+  __device__ __forceinline__ float x(int ii) const { float lo, hi; unpk2(x2[ii >> 1], lo, hi); return (ii & 1) ? hi : lo; }
+  __device__ __forceinline__ float y(int ii) const { float lo, hi; unpk2(y2[ii >> 1], lo, hi); return (ii & 1) ? hi : lo; }
+  __device__ __forceinline__ float z(int ii) const { float lo, hi; unpk2(z2[ii >> 1], lo, hi); return (ii & 1) ? hi : lo; }
 };
+
+__device__ __forceinline__ u64 fma2(u64 x, u64 y, u64 z) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(z));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 x, u64 y) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 x, u64 y) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  return d;
+}
+
+template <int P>
+__device__ __forceinline__ u64 powi2(u64 w) {
+  if constexpr (P == 1) {
+    return w;
+  } else if constexpr (P % 2 == 0) {
+    const u64 hf = powi2<P / 2>(w);
+    return mul2(hf, hf);
+  } else {
+    return mul2(w, powi2<P - 1>(w));
+  }
+}
 
 struct EAcc {
   float ev, scb, cob, chb;
+  u64 ev2, chb2;  // packed partial sums of the f32x2 path
 };
+
+// j-beads of a stage, laid out for the packed path: xy[j] = {-x, -x, -y, -y}, z[j] = {-z, -z}
+struct JDup {
+  const float4* xy;
+  const float2* z;
+};
+
+// Packed variant of pairs16 for the hot cases (no Gaussians, no self pairs; CHBM 0 or 1): the 8
+// i-beads are processed as 4 register pairs.
+template <int EVP, int CHBM>
+__device__ __forceinline__ void pairs16_packed(const JDup sjd, const int a, const int b, const int jj0,
+                                               IBeads& I, float (&cx)[2], float (&cy)[2], float (&cz)[2],
+                                               EAcc& E, const N3Consts& c) {
+  const u64 rs2 = pk2(c.ev_rs, c.ev_rs);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int jl = (((jj0 + k) ^ a) << 2) | b;
+    const float4 nxy = sjd.xy[jl];
+    const float2 nz = sjd.z[jl];
+    const u64 njx = pk2(nxy.x, nxy.y), njy = pk2(nxy.z, nxy.w), njz = pk2(nz.x, nz.y);
+    u64 ax = pk2(0.0f, 0.0f), ay = ax, az = ax;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const u64 dx = add2(I.x2[m], njx);
+      const u64 dy = add2(I.y2[m], njy);
+      const u64 dz = add2(I.z2[m], njz);
+      const u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+      float r2a, r2b;
+      unpk2(r2, r2a, r2b);
+      const u64 r = pk2(fast_sqrt(r2a), fast_sqrt(r2b));
+      const u64 q = fma2(rs2, r, r2);
+      float qa, qb;
+      unpk2(q, qa, qb);
+      const u64 wr = pk2(fast_rcp(qa), fast_rcp(qb));  // w / r
+      const u64 w = mul2(r, wr);
+      const u64 wp = powi2<EVP>(w);
+      E.ev2 = add2(E.ev2, wp);
+      u64 fs = mul2(wp, wr);
+      if (CHBM == 1) {
+        const u64 kc2 = pk2(c.chb_kc, c.chb_kc), one2 = pk2(1.0f, 1.0f), mone2 = pk2(-1.0f, -1.0f);
+        const u64 t = fma2(kc2, r2, fma2(mone2, r, one2));  // kC r^2 + 1 - r
+        E.chb2 = fma2(r2, t, E.chb2);
+        const u64 kc4 = pk2(4.0f * c.chb_kc, 4.0f * c.chb_kc), two2 = pk2(2.0f, 2.0f), m3 = pk2(-3.0f, -3.0f);
+        const u64 bb = fma2(m3, r, fma2(kc4, r2, two2));
+        const u64 nc = pk2(-c.chb_c, -c.chb_c);
+        fs = fma2(nc, bb, fs);
+      }
+      u64 t;
+      t = fma2(fs, dx, pk2(I.fx[2 * m], I.fx[2 * m + 1])); unpk2(t, I.fx[2 * m], I.fx[2 * m + 1]);
+      t = fma2(fs, dy, pk2(I.fy[2 * m], I.fy[2 * m + 1])); unpk2(t, I.fy[2 * m], I.fy[2 * m + 1]);
+      t = fma2(fs, dz, pk2(I.fz[2 * m], I.fz[2 * m + 1])); unpk2(t, I.fz[2 * m], I.fz[2 * m + 1]);
+      ax = fma2(fs, dx, ax);
+      ay = fma2(fs, dy, ay);
+      az = fma2(fs, dz, az);
+    }
+    float lo, hi;
+    unpk2(ax, lo, hi); cx[k] = lo + hi;
+    unpk2(ay, lo, hi); cy[k] = lo + hi;
+    unpk2(az, lo, hi); cz[k] = lo + hi;
+  }
+}
 
 // Two j-beads (registers jj0, jj0 + 1 of the XOR mapping) against this lane's 8 i-beads: 16 pairs.
 // GAUSS: evaluate the Gaussian block terms (runtime c.gk says which); CHBM: 0 none, 1 every pair
@@ -121,7 +235,7 @@ struct EAcc {
 template <int EVP, int GK, int CHBM, bool SELF>
 __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int a, const int b, const int jj0,
                                         IBeads& I, float (&cx)[2], float (&cy)[2], float (&cz)[2],
-                                        EAcc& E, const N3Consts& c, const float4* __restrict__ si4,
+                                        EAcc& E, const N3Consts& c, const int* __restrict__ si4,
                                         const int self_d) {
   constexpr bool GAUSS = GK != 0;
   constexpr bool kTypes = GAUSS || CHBM == 2;
@@ -138,7 +252,7 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
-      const float dx = I.x[ii] - pj.x, dy = I.y[ii] - pj.y, dz = I.z[ii] - pj.z;
+      const float dx = I.x(ii) - pj.x, dy = I.y(ii) - pj.y, dz = I.z(ii) - pj.z;
       float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
       bool self = false;
       if (SELF) {
@@ -157,7 +271,7 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
         fs = wp * wr;  // -(dE_ev/dr) / r in units of U
       }
       if (kTypes) {
-        const int ti = __float_as_int(si4[ii].w);
+        const int ti = si4[ii];
         const int xr = ti ^ tj;
         if (GAUSS) {
           float g = fast_ex2(r2 * c.g_c);
@@ -212,15 +326,17 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
 // with the warp's total for j-bead l of the tile (returned in out[3]).  WANT_J false (diagonal
 // stages, ordered pairs): the j side is dropped.
 template <int EVP, int GK, int CHBM, bool SELF, bool WANT_J>
-__device__ __forceinline__ void step64(const float4* __restrict__ sj, const int a, const int b, IBeads& I,
-                                       float (&out)[3], EAcc& E, const N3Consts& c,
-                                       const float4* __restrict__ si4, const int self_d) {
+__device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup sjd, const int a,
+                                       const int b, IBeads& I, float (&out)[3], EAcc& E, const N3Consts& c,
+                                       const int* __restrict__ si4, const int self_d) {
+  constexpr bool kPacked = N3_USE_F32X2 && EVP > 0 && GK == 0 && !SELF && CHBM <= 1;
   float s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;  // saved group (g even)
   float p0x = 0.f, p0y = 0.f, p0z = 0.f, p1x = 0.f, p1y = 0.f, p1z = 0.f;  // registers 0,1 after level "2"
 #pragma unroll 1
   for (int g = 0; g < 4; ++g) {
     float cx[2], cy[2], cz[2];
-    pairs16<EVP, GK, CHBM, SELF>(sj, a, b, 2 * g, I, cx, cy, cz, E, c, si4, self_d);
+    if constexpr (kPacked) pairs16_packed<EVP, CHBM>(sjd, a, b, 2 * g, I, cx, cy, cz, E, c);
+    else pairs16<EVP, GK, CHBM, SELF>(sj, a, b, 2 * g, I, cx, cy, cz, E, c, si4, self_d);
     if (!WANT_J) continue;
     if ((g & 1) == 0) {
       s0x = cx[0]; s0y = cy[0]; s0z = cz[0];
@@ -266,8 +382,10 @@ __device__ __forceinline__ void red_fixed(unsigned long long* p, float v, double
 template <int EVP, int GK, bool CHB>
 __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
   __shared__ __align__(16) float4 s_j[2][N3_JB];
+  __shared__ __align__(16) float4 s_jxy[2][N3_JB];
+  __shared__ __align__(8) float2 s_jz[2][N3_JB];
   __shared__ __align__(16) TileInfo s_jt[2][N3_STEPS];
-  __shared__ __align__(16) float4 s_i[N3_IB];
+  __shared__ int s_it[N3_IB];  // type bits of the i-block (slow variants)
   __shared__ float s_acc[N3_WARPS][3][N3_JB];
   __shared__ double s_red[4][N3_WARPS];
   __shared__ int s_item;
@@ -296,11 +414,17 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
     // the i-block: registers (positions) and shared memory (type bits for the slow variants)
     IBeads I;
 #pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {
-      const float4 p = A.pos4[ibase + iw + ii];
-      I.x[ii] = p.x; I.y[ii] = p.y; I.z[ii] = p.z;
-      I.fx[ii] = 0.0f; I.fy[ii] = 0.0f; I.fz[ii] = 0.0f;
-      if ((ii >> 1) == b) s_i[iw + ii] = p;
+    for (int m = 0; m < 4; ++m) {
+      const int64_t i0 = ibase + iw + 2 * m;  // even: the 8-byte loads are aligned
+      I.x2[m] = *reinterpret_cast<const u64*>(A.soa + i0);
+      I.y2[m] = *reinterpret_cast<const u64*>(A.soa + A.npad + i0);
+      I.z2[m] = *reinterpret_cast<const u64*>(A.soa + 2 * A.npad + i0);
+      I.fx[2 * m] = I.fy[2 * m] = I.fz[2 * m] = 0.0f;
+      I.fx[2 * m + 1] = I.fy[2 * m + 1] = I.fz[2 * m + 1] = 0.0f;
+      if (m == b) {
+        s_it[iw + 2 * m] = __float_as_int(A.pos4[i0].w);
+        s_it[iw + 2 * m + 1] = __float_as_int(A.pos4[i0 + 1].w);
+      }
     }
     // bounding box / chromosome range of the warp's 64 i-beads (two tiles); a padding-only tile
     // does not widen the box
@@ -318,7 +442,12 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
     const bool i_all_pad = ib.cmin >= MMM_PAD_CHROM;
 
     // first stage
-    s_j[0][tid] = A.pos4[(int64_t)js0 * N3_JB + tid];
+    {
+      const float4 p0 = A.pos4[(int64_t)js0 * N3_JB + tid];
+      s_j[0][tid] = p0;
+      s_jxy[0][tid] = make_float4(-p0.x, -p0.x, -p0.y, -p0.y);
+      s_jz[0][tid] = make_float2(-p0.z, -p0.z);
+    }
     if (tid < 2 * N3_STEPS)
       reinterpret_cast<float4*>(s_jt[0])[tid] = reinterpret_cast<const float4*>(A.tiles + (int64_t)js0 * N3_STEPS)[tid];
     __syncthreads();
@@ -339,16 +468,18 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
       const int self_base = (int)(ibase + iw - (int64_t)js * N3_JB);
       EAcc E;
       E.ev = E.scb = E.cob = E.chb = 0.0f;
+      E.ev2 = E.chb2 = pk2(0.0f, 0.0f);
 
       if (!i_all_pad) {
         for (int step = 0; step < N3_STEPS; ++step) {
           const TileInfo jt = s_jt[buf][step];
           if (jt.cmin >= MMM_PAD_CHROM) continue;  // padding only
           const float4* sj = s_j[buf] + step * MMM_TILE;
+          const JDup sjd = {s_jxy[buf] + step * MMM_TILE, s_jz[buf] + step * MMM_TILE};
           float fj[3];
           if (diag) {
             const int self_d = self_base - step * MMM_TILE;
-            step64<EVP, GK, CHB ? 2 : 0, true, false>(sj, a, b, I, fj, E, c, s_i + iw, self_d);
+            step64<EVP, GK, CHB ? 2 : 0, true, false>(sj, sjd, a, b, I, fj, E, c, s_it + iw, self_d);
             continue;  // ordered pairs: the j side is somebody's i side in this same stage pair
           }
           int chb_mode = 0;
@@ -366,13 +497,13 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
           }
           if (EVP == 0 && chb_mode == 0) continue;  // CHB-only pass: nothing to do for this tile pair
           if (near) {
-            step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+            step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
           } else if (!CHB || chb_mode == 0) {
-            step64<EVP, 0, 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+            step64<EVP, 0, 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
           } else if (chb_mode == 1) {
-            step64<EVP, 0, CHB ? 1 : 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+            step64<EVP, 0, CHB ? 1 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
           } else {
-            step64<EVP, 0, CHB ? 2 : 0, false, true>(sj, a, b, I, fj, E, c, s_i + iw, 0);
+            step64<EVP, 0, CHB ? 2 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
           }
           // lane (a, b) now holds j-bead 4 a + b = lane of this step; force on j is -sum
           const int col = step * MMM_TILE + lane;
@@ -380,6 +511,11 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
           s_acc[warp][1][col] -= fj[1];
           s_acc[warp][2][col] -= fj[2];
         }
+      }
+      {
+        float lo, hi;
+        unpk2(E.ev2, lo, hi); E.ev += lo + hi;
+        unpk2(E.chb2, lo, hi); E.chb += lo + hi;
       }
       const double wgt = diag ? 0.5 : 1.0;
       de0 += wgt * (double)E.ev;
@@ -389,6 +525,8 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
 
       if (more) {
         s_j[buf ^ 1][tid] = nxt;
+        s_jxy[buf ^ 1][tid] = make_float4(-nxt.x, -nxt.x, -nxt.y, -nxt.y);
+        s_jz[buf ^ 1][tid] = make_float2(-nxt.z, -nxt.z);
         if (tid < 2 * N3_STEPS) reinterpret_cast<float4*>(s_jt[buf ^ 1])[tid] = nxt_t;
       }
       __syncthreads();
@@ -529,6 +667,7 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   const PairParams& p = h->pp;
   N3Args A;
   A.pos4 = h->d_pos4;
+  A.soa = h->d_soa;
   A.tiles = h->d_tiles;
   A.facc = h->d_facc;
   A.epair = h->d_epair;

@@ -6,13 +6,13 @@
 #include "mmm_internal.cuh"
 
 // ---------------------------------------------------------------------------------------
-// prepare: one warp per tile. 24 B read + 16 B written per bead (+ 32 B per tile).
+// prepare: one warp per tile. 24 B read + 28 B written per bead (+ 32 B per tile).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_prepare(const double* __restrict__ x,
                                                  const double* __restrict__ center,
                                                  const int* __restrict__ type, int64_t n,
                                                  int64_t npad, float4* __restrict__ pos4,
-                                                 TileInfo* __restrict__ tiles,
+                                                 float* __restrict__ soa, TileInfo* __restrict__ tiles,
                                                  const int* __restrict__ skip) {
   if (skip && *skip) return;
   const int lane = threadIdx.x & 31;
@@ -30,6 +30,11 @@ __global__ void __launch_bounds__(256) k_prepare(const double* __restrict__ x,
     px = py = pz = MMM_PAD_COORD + MMM_PAD_STEP * (float)(i - n);
   }
   pos4[i] = make_float4(px, py, pz, __int_as_float(ty));
+  // plane copy x[], y[], z[]: the Newton-3 kernel loads its stationary beads as aligned register
+  // pairs (LDG.64 of two consecutive beads) for the f32x2 path
+  soa[i] = px;
+  soa[npad + i] = py;
+  soa[2 * npad + i] = pz;
 
   // bounding box over the real beads of the tile; an all-padding tile sits at the pad point
   const float big = 3.0e38f;
@@ -70,7 +75,7 @@ int mmm_launch_prepare(mmm_system* h, const int* d_skip) {
   const int warps_per_block = 8;
   const int64_t blocks = (h->ntiles + warps_per_block - 1) / warps_per_block;
   k_prepare<<<(unsigned)blocks, 256, 0, h->stream>>>(h->d_x, h->d_center, h->d_type, h->n, h->npad,
-                                                     h->d_pos4, h->d_tiles, d_skip);
+                                                     h->d_pos4, h->d_soa, h->d_tiles, d_skip);
   h->launches++;
   MMM_CUDA(h, cudaGetLastError());
   return MMM_OK;
