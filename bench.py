@@ -48,6 +48,12 @@ WORKLOADS = {
     "chrom": dict(key="S2_chrom", n_beads=50_000, chrom="chr1", region=None, n_loops=2_000,
                   flags=dict(SCB_USE_SUBCOMPARTMENT_BLOCKS=True),
                   name="single chromosome chr1, N=50000, EV+SCB+bonds+loops+angles, exact all-pairs"),
+    "stress": dict(key="S5_stress", n_beads=2_000_000, chrom=None, region=None, n_loops=100_000,
+                   flags=dict(SC_USE_SPHERICAL_CONTAINER=True, CHB_USE_CHROMOSOMAL_BLOCKS=True,
+                              SCB_USE_SUBCOMPARTMENT_BLOCKS=True, IBL_USE_B_LAMINA_INTERACTION=True,
+                              CF_USE_CENTRAL_FORCE=True, COB_USE_COMPARTMENT_BLOCKS=False, SHUFFLE_CHROMS=True),
+                   name="high-resolution genome-wide stress test, N=2000000, 22 chromosomes, EV+SCB+CHB+SC+LAM+CF+"
+                        "bonds+loops+angles, exact all-pairs"),
     "region": dict(key="S1_region", n_beads=10_000, chrom="chr1", region=(10_000_000, 110_000_000), n_loops=400,
                    flags=dict(), name="specific region chr1:10-110Mb, N=10000, EV+bonds+loops+angles, exact all-pairs"),
 }
@@ -254,8 +260,17 @@ def run_ours(opt):
 
     with tempfile.TemporaryDirectory(prefix="mmm_bench_") as tmp:
         t_build0 = time.perf_counter()
-        m = build_model(opt.workload, seed=replica_seed(rank), device=local, tmp=tmp)
+        decomposed = bool(opt.decompose) and world > 1
+        # replicas (default): rank r is ensemble member r.  --decompose: every rank builds the SAME
+        # system and the ranks share its pair work (one all-reduce per evaluation, mmm_dist.cu)
+        m = build_model(opt.workload, seed=0 if decomposed else replica_seed(rank), device=local, tmp=tmp)
         eng = m.engine
+        if decomposed:
+            from multimm_b200.engine import Engine
+
+            box = [Engine.dist_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            eng.dist_init(rank, world, box[0])
         build_s = time.perf_counter() - t_build0
         n = m.args.N_BEADS
 
@@ -273,7 +288,7 @@ def run_ours(opt):
             barrier()
         launches = eng.launch_count - launches0
         total_ms, pair_ms_max = max_over_ranks([total_ms, pair_ms], device=f"cuda:{local}")
-        value = whole_job_rate(world, K, total_ms)
+        value = whole_job_rate(1 if decomposed else world, K, total_ms)
 
         # ---- end to end through the C-ABI with host buffers ------------------------------------
         x_host = torch.from_numpy(m.positions.copy()).pin_memory()
@@ -290,7 +305,8 @@ def run_ours(opt):
             e_terms, forces = eng.energy_forces(out=f_np)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        e2e_value = whole_job_rate(world, K, 1e3 * max_over_ranks([e2e_s], device=f"cuda:{local}")[0])
+        e2e_value = whole_job_rate(1 if decomposed else world, K,
+                                   1e3 * max_over_ranks([e2e_s], device=f"cuda:{local}")[0])
 
         if rank != 0:
             m.close()
@@ -300,6 +316,8 @@ def run_ours(opt):
 
         # ---- rank 0 only: roofline, CPU baseline, a bounded minimisation ------------------------
         flops, pairs = pair_flops(m)
+        if decomposed:  # this rank's kernel evaluates 1 / world of the pairs
+            flops, pairs = flops / world, pairs / world
         peak_tflops, mufu_tops = measure_fp32_peak(local)
         pair_ms_avg = pair_ms / K
         achieved = flops / (pair_ms_avg * 1e-3) / 1e12
@@ -322,10 +340,13 @@ def run_ours(opt):
             mini = dict(max_iter=opt.minimize_iters, **rep)
         out = dict(
             metric="force_evals_per_s", value=value, unit="force_evals/s", n_gpus=world, steps=K, warmup=W,
-            ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+            ms_per_step=total_ms / K, higher_is_better=True, scaling="strong" if decomposed else "weak",
+            vs_baseline=None, dtype="f32",
             data="synthetic",
             config=dict(workload=w["name"], n_beads=n, n_loops=int(len(m.ms)), n_bonds=int(m.n_bonds),
-                        n_angles=int(m.n_angles), replicas=world, l2="flushed between steps (256 MiB memset inside "
+                        n_angles=int(m.n_angles), replicas=1 if decomposed else world,
+                        parallelism=(f"one system, pair work sharded over {world} GPUs, 1 NCCL all-reduce per evaluation"
+                                     if decomposed else f"{world} independent replica(s), no collective"), l2="flushed between steps (256 MiB memset inside "
                         "the timed region)", start="Hilbert lattice (0.1 nm)", build_seconds=build_s),
             clocks=clk.summary(),
             e2e=dict(value=e2e_value, unit="force_evals/s", h2d_bytes_per_step=24 * n,
@@ -381,6 +402,8 @@ def main():
     ap.add_argument("--workload", default="gw", choices=tuple(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--decompose", action="store_true",
+                    help="N > 1: one system whose pair work is shared by the ranks (default: one replica per rank)")
     ap.add_argument("--minimize-iters", type=int, default=50)
     opt = ap.parse_args()
     if opt.impl == "reference":

@@ -173,6 +173,20 @@ int mmm_evaluate_timed(mmm_handle h, int n, int flush_l2, float *total_ms, float
  * max_iter 0 = unlimited (the reference's default). No host round trip per iteration. */
 int mmm_minimize(mmm_handle h, double tol_kj_mol_nm, int64_t max_iter, mmm_min_report *out);
 
+/* ---- one system on several GPUs of one box (exact mode only) -------------------------------- */
+/* The reference has no multi-GPU path (DeviceIndex is never set, model.py:862-876).  Here the
+ * O(N^2) pair work of ONE system is dealt to `world` handles, one per GPU / process, each holding
+ * the full (replicated) state; one NCCL all-reduce of the fixed-point force planes and of the
+ * per-item energies follows the pair kernel of every evaluation.  All ranks must make the same
+ * calls in the same order.  Results are bit-identical to a single-GPU run.
+ *   rank 0: mmm_dist_unique_id(buf, 128); ship buf to the other ranks by any means;
+ *   every rank: mmm_dist_init(h, rank, world, buf, 128). */
+int mmm_dist_unique_id(void *out, int nbytes);
+int mmm_dist_init(mmm_handle h, int rank, int world, const void *unique_id, int nbytes);
+/* Single-GPU emulation of the sharding (tests): the shares of all `world` ranks are run one
+ * after another on this handle's GPU into the same accumulators. */
+int mmm_dist_emulate(mmm_handle h, int world);
+
 /* ---- introspection (tests, bench) ---------------------------------------------------- */
 /* Number of kernels this handle has launched since creation. */
 int64_t mmm_launch_count(mmm_handle h);

@@ -33,6 +33,7 @@ EXPORTS = (
     "mmm_hilbert_init", "mmm_hilbert_points",
     "mmm_energy_forces", "mmm_energy_forces_device", "mmm_evaluate_n", "mmm_evaluate_timed", "mmm_minimize",
     "mmm_launch_count", "mmm_set_pair_kernel", "mmm_pair_kernel_in_use", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_get_cell_grid", "mmm_measure_fp32_peak",
+    "mmm_dist_unique_id", "mmm_dist_init", "mmm_dist_emulate",
 )
 
 
@@ -97,6 +98,9 @@ def load():
         "mmm_get_cell_list": (i32, [vp, vp, vp]),
         "mmm_get_cell_grid": (i32, [vp, C.POINTER(C.c_float), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(i64)]),
         "mmm_measure_fp32_peak": (i32, [i32, C.POINTER(dbl), C.POINTER(dbl)]),
+        "mmm_dist_unique_id": (i32, [vp, i32]),
+        "mmm_dist_init": (i32, [vp, i32, i32, vp, i32]),
+        "mmm_dist_emulate": (i32, [vp, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

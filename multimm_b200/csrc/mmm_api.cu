@@ -39,7 +39,9 @@ static void derive_pair_params(mmm_system* h) {
   if (rc > 0.0f) {
     p.g_c = -1.4426950408889634f / (2.0f * rc * rc);
     p.g_inv_rc2 = 1.0f / (rc * rc);
-    p.rg2 = 2.0f * rc * rc * 40.0f * 0.6931471805599453f;  // exp(-rg^2 / 2rc^2) = 2^-40
+    // exp(-rg^2 / 2rc^2) = 2^-26: beyond rg a Gaussian term is < 1.5e-8 of its prefactor; the part of
+    // the term's total energy that lies beyond rg is < 1e-7 at chromatin density
+    p.rg2 = 2.0f * rc * rc * 26.0f * 0.6931471805599453f;
   } else {
     p.g_c = 0.0f; p.g_inv_rc2 = 0.0f; p.rg2 = 0.0f;
   }
@@ -130,6 +132,8 @@ int mmm_destroy(mmm_handle h) {
                   h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  mmm_dist_destroy(h);
+  if (h->d_epair_local) cudaFree(h->d_epair_local);
   if (h->h_done) cudaFreeHost(h->h_done);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->d_flush) cudaFree(h->d_flush);
@@ -407,6 +411,7 @@ static void free_scratch(mmm_system* h) {
   if (h->d_epair) { cudaFree(h->d_epair); h->d_epair = nullptr; }
   if (h->d_facc) { cudaFree(h->d_facc); h->d_facc = nullptr; }
   if (h->d_items) { cudaFree(h->d_items); h->d_items = nullptr; }
+  if (h->d_epair_local) { cudaFree(h->d_epair_local); h->d_epair_local = nullptr; }
   h->scratch_sig = -1;
 }
 
@@ -469,6 +474,11 @@ static int ensure_scratch(mmm_system* h) {
   }
   if ((rc = dev_alloc(h, &h->d_epair, (size_t)h->n_items * 4))) return rc;
   MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
+  if (h->nccl_comm) {
+    if (mode != 2) return mmm_fail(h, MMM_ERR_STATE, "the multi-GPU path needs the Newton-3 kernel: default functional forms, EV on, no cut-off");
+    if ((rc = dev_alloc(h, &h->d_epair_local, (size_t)h->n_items * 4))) return rc;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_epair_local, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
+  }
   h->scratch_sig = sig;
   return MMM_OK;
 }
@@ -488,7 +498,12 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
       if ((rc = mmm_launch_pair_exact(h, d_skip, &only_chb))) return rc;
     }
     rc = mmm_launch_pair_cutoff(h, d_skip);
-  } else if (h->pair_mode == 2) rc = mmm_launch_pair_n3(h, d_skip);
+  } else if (h->pair_mode == 2) {
+    rc = mmm_launch_pair_n3(h, d_skip);
+    // the one exchange step per evaluation (every rank enqueues it, converged or not, so that
+    // the collective can never be entered by some ranks only)
+    if (!rc && h->nccl_comm) rc = mmm_dist_allreduce(h);
+  }
   else if (h->pair_mode == 1) rc = mmm_launch_pair_exact(h, d_skip);
   if (rc) return rc;
   return mmm_launch_assemble(h, d_skip);

@@ -1,0 +1,129 @@
+// mmm_dist.cu — one large system on several B200s of one box, exact (NoCutoff) semantics.
+//
+// What shards: the O(N^2) pair work.  The Newton-3 kernel's work items (i-block x run of j-stages)
+// are dealt to the ranks round-robin (item k of rank r is item r + k * world), every rank
+// accumulates its share into its own fixed-point force planes and its own slots of the per-item
+// energy array, then ONE exchange step per evaluation follows:
+//     ncclAllReduce(force planes, uint64 sum)  +  ncclAllReduce(per-item energies, double sum)
+// over NVLink, enqueued on the handle's stream between the pair kernel and the O(N) pass.  Integer
+// sums are exact and every energy slot is written by exactly one rank (x + 0 + ... + 0), so all
+// ranks hold bit-identical forces and energies — the same bits a single GPU produces — and the
+// replicated O(N) state (positions, L-BFGS vectors, bonded/external pass) stays in lockstep
+// without any further communication: no host round trip per iteration here either.
+// What does not shard: the O(N) pass and the L-BFGS vector work (a few ms at N = 2e6 against
+// seconds of pair work); they are replicated.
+//
+// NCCL is opened with dlopen so that the library has no load-time dependency on it (single-GPU
+// users, the CPU build box).  mmm_dist_emulate runs the ranks' shares one after another on ONE
+// GPU into the same accumulators: the sharding logic is testable without a second GPU.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include "mmm_internal.cuh"
+
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi* nccl() {
+  static NcclApi api;
+  if (api.lib) return &api;
+  // a process that already imported torch has NCCL loaded under this soname; reuse it
+  api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!api.lib) return &api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+  return &api;
+}
+
+int nccl_fail(mmm_system* h, NcclApi* a, ncclResult_t r, const char* what) {
+  return mmm_fail(h, MMM_ERR_CUDA, std::string("CUDA error: NCCL ") + what + ": " + (a->GetErrorString ? a->GetErrorString(r) : "?"));
+}
+
+}  // namespace
+
+// The exchange step: called by mmm_evaluate after the pair kernel when a communicator exists.
+int mmm_dist_allreduce(mmm_system* h) {
+  NcclApi* a = nccl();
+  ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+  ncclResult_t r = a->AllReduce(h->d_facc, h->d_facc, 3 * (size_t)h->npad, ncclUint64, ncclSum, comm, h->stream);
+  if (r != ncclSuccess) return nccl_fail(h, a, r, "all-reduce of the force planes");
+  r = a->AllReduce(h->d_epair_local, h->d_epair, (size_t)h->n_items * 4, ncclDouble, ncclSum, comm, h->stream);
+  if (r != ncclSuccess) return nccl_fail(h, a, r, "all-reduce of the energies");
+  return MMM_OK;
+}
+
+void mmm_dist_destroy(mmm_system* h) {
+  if (h->nccl_comm) {
+    NcclApi* a = nccl();
+    if (a->ok) a->CommDestroy((ncclComm_t)h->nccl_comm);
+    h->nccl_comm = nullptr;
+  }
+}
+
+extern "C" {
+
+int mmm_dist_unique_id(void* out, int nbytes) {
+  if (!out || nbytes < (int)sizeof(ncclUniqueId)) return MMM_ERR_ARG;
+  NcclApi* a = nccl();
+  if (!a->ok) return mmm_fail(nullptr, MMM_ERR_CUDA, "CUDA error: NCCL (libnccl.so.2) could not be loaded");
+  ncclUniqueId id;
+  ncclResult_t r = a->GetUniqueId(&id);
+  if (r != ncclSuccess) return mmm_fail(nullptr, MMM_ERR_CUDA, std::string("CUDA error: NCCL ncclGetUniqueId: ") + a->GetErrorString(r));
+  memcpy(out, &id, sizeof(id));
+  return MMM_OK;
+}
+
+int mmm_dist_init(mmm_handle h, int rank, int world, const void* unique_id, int nbytes) {
+  if (!h) return MMM_ERR_ARG;
+  if (world < 1 || rank < 0 || rank >= world) return mmm_fail(h, MMM_ERR_ARG, "mmm_dist_init: need 0 <= rank < world");
+  if (h->cutoff > 0.0) return mmm_fail(h, MMM_ERR_STATE, "mmm_dist_init: the sharded path is the exact (NoCutoff) one; set the cut-off to 0");
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  mmm_dist_destroy(h);
+  h->dist_emulate = false;
+  h->dist_rank = rank;
+  h->dist_world = world;
+  if (world > 1) {
+    if (!unique_id || nbytes < (int)sizeof(ncclUniqueId)) return mmm_fail(h, MMM_ERR_ARG, "mmm_dist_init: unique id missing");
+    NcclApi* a = nccl();
+    if (!a->ok) return mmm_fail(h, MMM_ERR_CUDA, "CUDA error: NCCL (libnccl.so.2) could not be loaded");
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    ncclComm_t comm;
+    ncclResult_t r = a->CommInitRank(&comm, world, id, rank);
+    if (r != ncclSuccess) return nccl_fail(h, a, r, "ncclCommInitRank");
+    h->nccl_comm = comm;
+  }
+  h->scratch_sig = -2;  // re-size the scratch (local energy slots)
+  return MMM_OK;
+}
+
+int mmm_dist_emulate(mmm_handle h, int world) {
+  if (!h) return MMM_ERR_ARG;
+  if (world < 1) return mmm_fail(h, MMM_ERR_ARG, "mmm_dist_emulate: world must be >= 1");
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  mmm_dist_destroy(h);
+  h->dist_rank = 0;
+  h->dist_world = world;
+  h->dist_emulate = world > 1;
+  h->scratch_sig = -2;
+  return MMM_OK;
+}
+
+}  // extern "C"

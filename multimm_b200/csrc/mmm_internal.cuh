@@ -50,7 +50,7 @@ struct PairParams {
   float ev_pref;    // eps * sigma^p
   float g_c;        // -log2(e) / (2 rc^2): exp(-r^2/(2 rc^2)) = ex2(r2 * g_c)
   float g_inv_rc2;  // 1 / rc^2
-  float rg2;        // squared range beyond which the Gaussian block terms are < 2^-40
+  float rg2;        // squared range beyond which the Gaussian block terms are < 2^-26
   float cutoff2;    // cutoff^2 (cutoff mode) or 0
 };
 
@@ -154,6 +154,11 @@ struct mmm_system {
   int pair_kernel_pref = 0;      // 0 auto, 1 force the gather kernel (tests / A-B timing)
   unsigned long long* d_facc = nullptr;  // [3][npad] fixed-point force accumulator (Newton-3, cells)
   int2* d_items = nullptr;       // Newton-3 work items
+  // several GPUs, one system (mmm_dist.cu): Newton-3 items are dealt round-robin to the ranks
+  int dist_rank = 0, dist_world = 1;
+  bool dist_emulate = false;     // run every rank's share on this GPU, one after another (tests)
+  void* nccl_comm = nullptr;
+  double* d_epair_local = nullptr;  // this rank's energy slots before the all-reduce (dist only)
   int n3_items = 0;              // number of Newton-3 work items (their energy slots come first in d_epair)
   bool n3_chb_only = false;      // the item list is the cut-off mode's CHB-only list
   std::vector<int32_t> h_chrom;  // host copy of the chromosome ids (static; sizes the CHB-only item list)
@@ -219,6 +224,9 @@ bool mmm_pair_fast_path_pp(const PairParams& p);
 bool mmm_pair_n3_eligible(const mmm_system* h);
 int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, bool chb_only);
 int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only = false);  // d_pos4 -> d_facc, d_epair
+// mmm_dist.cu
+int mmm_dist_allreduce(mmm_system* h);
+void mmm_dist_destroy(mmm_system* h);
 // mmm_cells.cu
 int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip);
 int64_t mmm_cells_energy_slots(const mmm_system* h);

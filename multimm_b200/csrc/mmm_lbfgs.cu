@@ -377,6 +377,9 @@ int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report
     const double per_eval = tb / batch;
     int want = (int)(0.05 / (per_eval > 1e-6 ? per_eval : 1e-6));
     batch = want < 4 ? 4 : (want > 512 ? 512 : want);
+    // several GPUs: every rank must enqueue the same number of evaluations (each contains a
+    // collective), so the batch size may not depend on this rank's clock
+    if (h->nccl_comm) batch = 8;
   }
   // a failed line search leaves a pending RESTORE (x <- xp)
   k_apply<<<grid_apply, 256, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_xp, h->d_gp, h->d_d, h->d_S, h->d_Y);

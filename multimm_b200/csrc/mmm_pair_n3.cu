@@ -29,7 +29,7 @@
 //   energies: FP32 within a stage, FP64 across stages, one slot per item (fixed order).
 //
 // Tile classification is warp-uniform, from the 32-bead bounding boxes / chromosome ranges of
-// k_prepare: far tiles skip the Gaussians (< 2^-40 of their prefactor), CHB only where the
+// k_prepare: far tiles skip the Gaussians (< 2^-26 of their prefactor), CHB only where the
 // chromosome ranges overlap, per-pair chromosome compare only when a tile is not
 // single-chromosome.  The hot variant (far, no CHB) is 21 FP32-pipe/MUFU instructions per
 // unordered pair: 3 FADD, FMUL + 2 FFMA (r^2), MUFU.SQRT, FFMA (q = r^2 + r_s r), MUFU.RCP
@@ -104,6 +104,7 @@ struct N3Args {
   const int* skip;
   int64_t npad;
   int n_items;
+  int item_first, item_stride;  // this launch handles items item_first + k * item_stride
   double fscale;             // U * 2^24
   double e_ev, e_gauss, e_chb;  // energy prefactors: eps sigma^p; -rc^2 U; dE
   N3Consts c;
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
     __syncthreads();  // protects s_item, s_i, s_j, s_red across items
     if (tid == 0) s_item = atomicAdd(A.counter, 1);
     __syncthreads();
-    const int item = s_item;
+    const int item = A.item_first + s_item * A.item_stride;
     if (item >= A.n_items) break;
     const int2 it = A.items[item];
     const int iblk = it.x, js0 = it.y & 0xFFFFFF, js1 = js0 + (it.y >> 24);
@@ -497,7 +498,9 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
           }
           if (EVP == 0 && chb_mode == 0) continue;  // CHB-only pass: nothing to do for this tile pair
           if (near) {
-            step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+            if (!CHB || chb_mode == 0) step64<EVP, GK, 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+            else if (chb_mode == 1) step64<EVP, GK, CHB ? 1 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+            else step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
           } else if (!CHB || chb_mode == 0) {
             step64<EVP, 0, 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
           } else if (chb_mode == 1) {
@@ -591,7 +594,8 @@ int launch_n3(mmm_system* h, const N3Args& A) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pair_n3<EVP, GK, CHB>, N3_THREADS, 0);
   if (occ < 1) occ = 1;
   int grid = h->sm_count * occ;
-  if (grid > A.n_items) grid = A.n_items;
+  const int n_local = (A.n_items - A.item_first + A.item_stride - 1) / A.item_stride;
+  if (grid > n_local) grid = n_local > 0 ? n_local : 1;
   k_pair_n3<EVP, GK, CHB><<<grid, N3_THREADS, 0, h->stream>>>(A);
   return 0;
 }
@@ -670,7 +674,7 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   A.soa = h->d_soa;
   A.tiles = h->d_tiles;
   A.facc = h->d_facc;
-  A.epair = h->d_epair;
+  A.epair = h->nccl_comm ? h->d_epair_local : h->d_epair;
   A.items = h->d_items;
   A.counter = h->d_counter;
   A.skip = d_skip;
@@ -703,7 +707,6 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   A.e_gauss = -(rc * rc) * U;
   A.e_chb = (double)p.chb_de;
 
-  MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
   const bool timed = !chb_only;  // the CHB-only pass is timed with the cell-list pass
   const bool collect = timed && h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
   cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
@@ -711,10 +714,17 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   if (collect) h->ev_cursor++;
   if (timed) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
   const bool chb = p.chb_form >= 0;
-  if (chb_only) launch_n3<0, 0, true>(h, A);
-  else if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
-  else launch_n3_evp<3>(h, A, c.gk, chb);
-  h->launches++;
+  // one launch for this rank's share of the items; in emulation every rank's share in turn
+  const int r0 = h->dist_emulate ? 0 : h->dist_rank, r1 = h->dist_emulate ? h->dist_world : h->dist_rank + 1;
+  for (int r = r0; r < r1; ++r) {
+    A.item_first = r;
+    A.item_stride = h->dist_world;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
+    if (chb_only) launch_n3<0, 0, true>(h, A);
+    else if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
+    else launch_n3_evp<3>(h, A, c.gk, chb);
+    h->launches++;
+  }
   MMM_CUDA(h, cudaGetLastError());
   if (timed) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;

@@ -164,6 +164,26 @@ class Engine:
         self._ck(self._lib.mmm_minimize(self._h, float(tol), int(max_iter), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in MinReport._fields_}
 
+    # -- one system on several GPUs (exact mode) ------------------------------------------------
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        """NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        rc = lib.mmm_dist_unique_id(buf, 128)
+        if rc != 0:
+            raise Error(rc, lib.mmm_last_error(None).decode())
+        return buf.raw
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes | None):
+        """Join a group of `world` engines (one per GPU / process) that share the pair work of ONE system."""
+        buf = C.create_string_buffer(unique_id, 128) if unique_id else None
+        self._ck(self._lib.mmm_dist_init(self._h, int(rank), int(world), buf, 128 if unique_id else 0))
+
+    def dist_emulate(self, world: int):
+        """Tests: run the shares of `world` ranks one after another on this GPU."""
+        self._ck(self._lib.mmm_dist_emulate(self._h, int(world)))
+
     # -- introspection ----------------------------------------------------------------------
     @property
     def launch_count(self) -> int:
