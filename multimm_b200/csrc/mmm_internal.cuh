@@ -17,7 +17,10 @@ constexpr int MMM_TILE = 32;          // beads per tile (one warp's worth); bbox
 constexpr int MMM_IBLOCK = 256;       // i-beads per work item of the exact pair kernel
 constexpr int MMM_STAGE = 256;        // j-beads staged in shared memory at a time
 constexpr int MMM_ASM_BLOCK = 128;    // threads per block of the O(N) assemble kernel
-constexpr int MMM_LBFGS_M = 6;        // history length (liblbfgs default used by OpenMM)
+#ifndef MMM_LBFGS_M_VALUE
+#define MMM_LBFGS_M_VALUE 6
+#endif
+constexpr int MMM_LBFGS_M = MMM_LBFGS_M_VALUE;  // history length (6 = liblbfgs default used by OpenMM)
 constexpr int MMM_NDOT = 6 * MMM_LBFGS_M + 7;  // dot products per evaluation (vector-free L-BFGS)
 constexpr int MMM_PAD_TO = 512;       // npad is a multiple of this (i-block of the Newton-3 pair kernel)
 // Padding bead k (k = i - n < MMM_PAD_TO) sits at x = y = z = MMM_PAD_COORD + k * MMM_PAD_STEP, so
