@@ -173,6 +173,27 @@ int mmm_evaluate_timed(mmm_handle h, int n, int flush_l2, float *total_ms, float
  * max_iter 0 = unlimited (the reference's default). No host round trip per iteration. */
 int mmm_minimize(mmm_handle h, double tol_kj_mol_nm, int64_t max_iter, mmm_min_report *out);
 
+/* ---- MD relaxation (model.py:768-808 integrators, model.py:907-995 run_md) -------------------- */
+#define MMM_MD_LANGEVIN 0 /* mm.LangevinIntegrator(T, friction, dt)   model.py:781-787 */
+#define MMM_MD_VERLET 1   /* mm.VerletIntegrator(dt)                  model.py:770-772 */
+#define MMM_MD_BROWNIAN 2 /* mm.BrownianIntegrator(T, friction, dt)   model.py:801-807 */
+typedef struct {
+  int64_t step;        /* steps taken since mmm_md_configure */
+  double potential;    /* kJ/mol at the current positions */
+  double kinetic;      /* 1/2 m sum v^2, kJ/mol (leapfrog velocities) */
+  double temperature;  /* 2 K / (3 N kB), K */
+} mmm_md_report;
+/* mass_amu: the single bead mass of forcefields/ff.xml:5 (16427.889). seed: noise stream. */
+int mmm_md_configure(mmm_handle h, int integrator, double dt_ps, double temperature_k,
+                     double friction_per_ps, double mass_amu, uint64_t seed);
+/* context.setVelocitiesToTemperature(T, seed), model.py:878. */
+int mmm_set_velocities_to_temperature(mmm_handle h, double temperature_k, uint64_t seed);
+int mmm_set_velocities(mmm_handle h, const double *v_nm_ps /* N x 3 */);
+int mmm_get_velocities(mmm_handle h, double *v_out);
+/* simulation.step(n) + getState(getEnergy=True), model.py:929-936: n steps enqueued back to back
+ * (one fused force evaluation + one integrator launch each), energies read once at the end. */
+int mmm_md_run(mmm_handle h, int64_t n_steps, mmm_md_report *out);
+
 /* ---- one system on several GPUs of one box (exact mode only) -------------------------------- */
 /* The reference has no multi-GPU path (DeviceIndex is never set, model.py:862-876).  Here the
  * O(N^2) pair work of ONE system is dealt to `world` handles, one per GPU / process, each holding

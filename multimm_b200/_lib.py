@@ -34,6 +34,7 @@ EXPORTS = (
     "mmm_energy_forces", "mmm_energy_forces_device", "mmm_evaluate_n", "mmm_evaluate_timed", "mmm_minimize",
     "mmm_launch_count", "mmm_set_pair_kernel", "mmm_pair_kernel_in_use", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_get_cell_grid", "mmm_measure_fp32_peak",
     "mmm_dist_unique_id", "mmm_dist_init", "mmm_dist_emulate",
+    "mmm_md_configure", "mmm_set_velocities_to_temperature", "mmm_set_velocities", "mmm_get_velocities", "mmm_md_run",
 )
 
 
@@ -43,6 +44,13 @@ class MinReport(C.Structure):
         ("e_initial", C.c_double), ("e_final", C.c_double), ("rms_force", C.c_double),
         ("wall_seconds", C.c_double), ("converged", C.c_int32), ("ls_status", C.c_int32),
     ]
+
+
+class MdReport(C.Structure):
+    _fields_ = [("step", C.c_int64), ("potential", C.c_double), ("kinetic", C.c_double), ("temperature", C.c_double)]
+
+
+MD_INTEGRATORS = {"langevin": 0, "verlet": 1, "brownian": 2}
 
 
 class Error(RuntimeError):
@@ -101,6 +109,11 @@ def load():
         "mmm_dist_unique_id": (i32, [vp, i32]),
         "mmm_dist_init": (i32, [vp, i32, i32, vp, i32]),
         "mmm_dist_emulate": (i32, [vp, i32]),
+        "mmm_md_configure": (i32, [vp, i32, dbl, dbl, dbl, dbl, C.c_uint64]),
+        "mmm_set_velocities_to_temperature": (i32, [vp, dbl, C.c_uint64]),
+        "mmm_set_velocities": (i32, [vp, vp]),
+        "mmm_get_velocities": (i32, [vp, vp]),
+        "mmm_md_run": (i32, [vp, i64, C.POINTER(MdReport)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

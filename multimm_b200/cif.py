@@ -134,3 +134,53 @@ def write_psf(n: int, path, title="No title provided"):
         f.writelines(atoms)
         f.writelines(["\n", f"{n - 1:>8} !NBOND: bonds\n"])
         f.writelines(bonds)
+
+
+class DCDWriter:
+    """Minimal CHARMM/NAMD DCD trajectory writer (what OpenMM's DCDReporter produces for
+    model.py:920-925): little-endian, no unit cell, coordinates in Angstrom as float32."""
+
+    def __init__(self, path, n_atoms: int, dt_ps: float, interval: int, first_step: int = 0):
+        self.fh = open(path, "wb")
+        self.n_atoms, self.frames = int(n_atoms), 0
+        icntrl = np.zeros(20, dtype="<i4")
+        icntrl[1], icntrl[2] = first_step, interval
+        icntrl[9] = np.array([dt_ps / 0.04888821], dtype="<f4").view("<i4")[0]  # AKMA time units
+        icntrl[19] = 24
+        title = b"Created by multimm_b200".ljust(80)
+        self.fh.write(np.array([84], "<i4").tobytes() + b"CORD" + icntrl.tobytes() + np.array([84], "<i4").tobytes())
+        self.fh.write(np.array([84, 1], "<i4").tobytes() + title + np.array([84], "<i4").tobytes())
+        self.fh.write(np.array([4, self.n_atoms, 4], "<i4").tobytes())
+
+    def write(self, coords_angstrom):
+        c = np.asarray(coords_angstrom, dtype="<f4")
+        if c.shape != (self.n_atoms, 3):
+            raise ValueError("DCD frame has the wrong shape")
+        nb = np.array([4 * self.n_atoms], "<i4").tobytes()
+        for d in range(3):
+            self.fh.write(nb + np.ascontiguousarray(c[:, d]).tobytes() + nb)
+        self.frames += 1
+        pos = self.fh.tell()
+        self.fh.seek(8)  # NSET, first control word after 'CORD'
+        self.fh.write(np.array([self.frames], "<i4").tobytes())
+        self.fh.seek(pos)
+
+    def close(self):
+        self.fh.close()
+
+
+def read_dcd(path):
+    """Frames of a DCD written by DCDWriter -> (n_frames, n_atoms, 3) float32 (tests)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    n_frames = int(raw[8:12].view("<i4")[0])
+    off = 4 + 84 + 4
+    ntitle_block = int(raw[off:off + 4].view("<i4")[0])
+    off += 4 + ntitle_block + 4
+    n_atoms = int(raw[off + 4:off + 8].view("<i4")[0])
+    off += 12
+    out = np.empty((n_frames, n_atoms, 3), dtype=np.float32)
+    for f in range(n_frames):
+        for d in range(3):
+            out[f, :, d] = raw[off + 4:off + 4 + 4 * n_atoms].view("<f4")
+            off += 8 + 4 * n_atoms
+    return out

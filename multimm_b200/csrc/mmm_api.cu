@@ -129,7 +129,7 @@ int mmm_destroy(mmm_handle h) {
                   h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_soa, h->d_tiles, h->d_g,
                   h->d_fpair, h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
-                  h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs};
+                  h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs, h->d_v};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   mmm_dist_destroy(h);

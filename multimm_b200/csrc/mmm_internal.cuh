@@ -179,6 +179,14 @@ struct mmm_system {
   double *d_S = nullptr, *d_Y = nullptr;  // [m][3n]
   int* h_done = nullptr;         // pinned mirror of LbfgsState::done / counters
 
+  // MD relaxation (mmm_md.cu)
+  double* d_v = nullptr;         // [3n] velocities, nm/ps
+  bool md_configured = false;
+  int md_integrator = 0;
+  double md_dt = 0.001, md_temperature = 310.0, md_gamma = 0.5, md_mass = 16427.889;
+  uint64_t md_seed = 0;
+  int64_t md_step = 0;
+
   // cell list (cutoff mode)
   uint32_t* d_keys = nullptr;    // [n] sorted keys
   int* d_order = nullptr;        // [n] sorted bead order

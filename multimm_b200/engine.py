@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Error, MinReport, NUM_TERMS, TERM, TERM_NAMES  # noqa: F401  (re-exported)
+from ._lib import Error, MdReport, MinReport, NUM_TERMS, TERM, TERM_NAMES  # noqa: F401  (re-exported)
 
 
 def _p(a):
@@ -163,6 +163,34 @@ class Engine:
         rep = MinReport()
         self._ck(self._lib.mmm_minimize(self._h, float(tol), int(max_iter), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in MinReport._fields_}
+
+    # -- MD relaxation ----------------------------------------------------------------------------
+    def md_configure(self, integrator="langevin", dt_ps=0.001, temperature_k=310.0, friction_per_ps=0.5,
+                     mass_amu=16427.889, seed=0):
+        kind = _lib.MD_INTEGRATORS.get(integrator, integrator) if isinstance(integrator, str) else int(integrator)
+        if not isinstance(kind, int):
+            raise ValueError(f"Unknown SIM_INTEGRATOR_TYPE: {integrator} (supported: langevin, verlet, brownian)")
+        self._ck(self._lib.mmm_md_configure(self._h, kind, float(dt_ps), float(temperature_k), float(friction_per_ps),
+                                            float(mass_amu), int(seed)))
+
+    def set_velocities_to_temperature(self, temperature_k: float, seed: int = 0):
+        self._ck(self._lib.mmm_set_velocities_to_temperature(self._h, float(temperature_k), int(seed)))
+
+    def set_velocities(self, v):
+        v = _arr(v, np.float64)
+        if v.shape != (self.n, 3):
+            raise ValueError(f"velocities must have shape ({self.n}, 3)")
+        self._ck(self._lib.mmm_set_velocities(self._h, _p(v)))
+
+    def get_velocities(self) -> np.ndarray:
+        out = np.empty((self.n, 3), dtype=np.float64)
+        self._ck(self._lib.mmm_get_velocities(self._h, _p(out)))
+        return out
+
+    def md_run(self, n_steps: int) -> dict:
+        rep = MdReport()
+        self._ck(self._lib.mmm_md_run(self._h, int(n_steps), C.byref(rep)))
+        return {k: getattr(rep, k) for k, _ in MdReport._fields_}
 
     # -- one system on several GPUs (exact mode) ------------------------------------------------
     @staticmethod

@@ -30,6 +30,9 @@ CHROM_LENGTHS = np.array(_LENGTHS, dtype=np.int64)
 CHROM_SIZES = {CHROM_NAMES[i]: _LENGTHS[i] for i in range(24)}
 
 
+BEAD_MASS = 16427.889  # amu, the one atom type of forcefields/ff.xml:5
+
+
 def _minmax(a):
     a = np.nan_to_num(np.asarray(a, dtype=np.float64))
     return (a - a.min()) / (a.max() - a.min())

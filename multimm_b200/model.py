@@ -7,8 +7,8 @@
 Everything that was an OpenMM object is now one ``Engine`` handle on a B200: the ``add_*``
 methods pack the same parameters, read from the same config fields, into bulk C-ABI calls
 (one call per term instead of one SWIG call per particle), ``min_energy`` runs the on-device
-L-BFGS, and the structure files are written in the reference's formats.  Out of scope here (see
-DESIGN.md): MD relaxation, plots, nucleosome interpolation.
+L-BFGS, ``run_md`` the on-device integrators, and the structure files are written in the reference's
+formats.  Out of scope here: plots, nucleosome interpolation.
 """
 from __future__ import annotations
 
@@ -269,6 +269,57 @@ class MultiMM:
         logger.info(f"--- Energy minimization done!! Executed in {dt // 3600:.0f} hours, {dt % 3600 // 60:.0f} "
                     f"minutes and  {dt % 60:.0f} seconds. :D --- {self.report}")
 
+    def run_md(self):
+        """model.py:907-995: relaxation with the configured integrator, a thermodynamic record every
+        SIM_SAMPLING_STEP steps (printed like OpenMM's StateDataReporter), a CIF per sample in
+        md_frames/, a DCD every SIM_N_STEPS // TRJ_FRAMES steps, model/MultiMM_afterMD.cif at the end."""
+        a = self.args
+        kind = str(a.SIM_INTEGRATOR_TYPE).lower()
+        if kind not in _lib.MD_INTEGRATORS:
+            raise ValueError(f"SIM_INTEGRATOR_TYPE={a.SIM_INTEGRATOR_TYPE!r} is not available "
+                             f"(supported: {', '.join(_lib.MD_INTEGRATORS)})")
+        dt = _f(a.SIM_INTEGRATOR_STEP)  # ps
+        temp = _f(a.SIM_TEMPERATURE)
+        seed = int(a.SHUFFLING_SEED)
+        self.engine.md_configure(kind, dt, temp, float(a.SIM_FRICTION_COEFF), loaders.BEAD_MASS, seed)
+        self.engine.set_velocities_to_temperature(temp, seed)  # model.py:878
+        self.md_history = {"step": [], "potential": [], "kinetic": [], "total": [], "temperature": []}
+        n_steps, every = int(a.SIM_N_STEPS), max(1, int(a.SIM_SAMPLING_STEP))
+        dcd_every = max(1, n_steps // max(1, int(a.TRJ_FRAMES)))
+        dcd = cif.DCDWriter(self.save_path + "metadata/MultiMM_annealing.dcd", a.N_BEADS, dt, dcd_every)
+        chunk = int(np.gcd(every, dcd_every))
+        t0 = time.time()
+        print('#"Step"\t"Potential Energy (kJ/mole)"\t"Kinetic Energy (kJ/mole)"\t"Total Energy (kJ/mole)"\t"Temperature (K)"')
+        done = 0
+        try:
+            while done < (n_steps // every) * every:
+                rep = self.engine.md_run(chunk)
+                done += chunk
+                want_frame, want_dcd = done % every == 0, done % dcd_every == 0
+                if want_frame or want_dcd:
+                    self.positions = self.engine.get_positions()
+                if want_dcd:
+                    dcd.write(10.0 * self.positions)
+                if want_frame:
+                    h = self.md_history
+                    h["step"].append(done); h["potential"].append(rep["potential"]); h["kinetic"].append(rep["kinetic"])
+                    h["total"].append(rep["potential"] + rep["kinetic"]); h["temperature"].append(rep["temperature"])
+                    print(f"{done}\t{rep['potential']}\t{rep['kinetic']}\t{rep['potential'] + rep['kinetic']}\t{rep['temperature']}")
+                    cif.write_mmcif(10.0 * self.positions, self.chr_ends,
+                                    self.save_path + f"md_frames/frame_{done // every}.cif", hetatm_ends=True,
+                                    connections=False, decimals=4)
+        finally:
+            dcd.close()
+        self.positions = self.engine.get_positions()
+        cif.write_mmcif(10.0 * self.positions, self.chr_ends, self.save_path + "model/MultiMM_afterMD.cif",
+                        hetatm_ends=True, connections=False, decimals=4)
+        with open(self.save_path + "metadata/md_thermodynamics.tsv", "w") as fh:
+            fh.write("step\tpotential\tkinetic\ttotal\ttemperature\n")
+            for row in zip(*(self.md_history[k] for k in ("step", "potential", "kinetic", "total", "temperature"))):
+                fh.write("\t".join(str(v) for v in row) + "\n")
+        self.timings["md_s"] = time.time() - t0
+        logger.info(f"MD finished in {self.timings['md_s']:.1f} s ({n_steps} steps, {kind})")
+
     def save_chromosomes(self):
         """model.py:899-905."""
         for k in range(len(self.chr_ends) - 1):
@@ -296,7 +347,7 @@ class MultiMM:
         if self._whole:
             self.save_chromosomes()
         if self.args.SIM_RUN_MD:
-            logger.warning("SIM_RUN_MD is set but MD relaxation is outside this engine's scope; skipped")
+            self.run_md()
         self.save_args_to_txt(self.args.OUT_PATH + "/metadata/parameters.txt")
         return self.report
 

@@ -1,0 +1,136 @@
+"""MD relaxation on the GPU against numpy restatements of the integrators
+([OpenMM] LangevinIntegrator / VerletIntegrator / BrownianIntegrator) driven by the oracle's forces
+and by the same Philox4x32-10 noise stream."""
+import os
+
+import numpy as np
+import pytest
+
+from common import O, make_case, to_engine, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+KB = 0.008314462618
+MASS = 16427.889
+
+
+def philox4x32_10(c, k):
+    """c: (n,4) uint32 counters, k: (2,) uint32 key -> (n,4) uint32."""
+    c = c.astype(np.uint64).copy()
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[:, 0]
+        p1 = np.uint64(0xCD9E8D57) * c[:, 2]
+        n0 = (p1 >> np.uint64(32)) ^ c[:, 1] ^ k0
+        n1 = p1 & m32
+        n2 = (p0 >> np.uint64(32)) ^ c[:, 3] ^ k1
+        n3 = p0 & m32
+        c = np.stack([n0, n1, n2, n3], axis=1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return c.astype(np.uint32)
+
+
+def normals3(seed, n, step, stream):
+    c = np.zeros((n, 4), dtype=np.uint32)
+    c[:, 0] = np.arange(n, dtype=np.uint32)
+    c[:, 1] = step & 0xFFFFFFFF
+    c[:, 2] = step >> 32
+    c[:, 3] = stream
+    u = (philox4x32_10(c, (seed & 0xFFFFFFFF, seed >> 32)).astype(np.float64) + 0.5) / 4294967296.0
+    r0, r1 = np.sqrt(-2.0 * np.log(u[:, 0])), np.sqrt(-2.0 * np.log(u[:, 2]))
+    return np.stack([r0 * np.cos(2 * np.pi * u[:, 1]), r0 * np.sin(2 * np.pi * u[:, 1]), r1 * np.cos(2 * np.pi * u[:, 3])], axis=1)
+
+
+def test_initial_velocities_are_maxwell_boltzmann_and_reproducible(built_lib):
+    case = make_case(20000, terms=("EV",), seed=1)
+    eng = to_engine(case)
+    eng.set_velocities_to_temperature(310.0, seed=7)
+    v = eng.get_velocities()
+    assert np.allclose(v, np.sqrt(KB * 310.0 / MASS) * normals3(7, 20000, 0, 0), rtol=1e-12, atol=1e-15)
+    temp = MASS * (v ** 2).sum() / (3 * 20000 * KB)
+    assert abs(temp - 310.0) < 0.02 * 310.0  # 1/sqrt(3N/2) = 0.6 %
+    eng.set_velocities_to_temperature(310.0, seed=8)
+    assert not np.array_equal(v, eng.get_velocities())
+    eng.close()
+
+
+@pytest.mark.parametrize("integrator", ["verlet", "langevin", "brownian"])
+def test_steps_match_numpy_restatement(built_lib, integrator):
+    """Three steps of each integrator: positions and velocities against numpy with the ORACLE's forces."""
+    case = make_case(400, n_chrom=2, seed=5, noise=0.02)
+    sysd = to_oracle(case)
+    eng = to_engine(case)
+    dt, temp, gamma, seed = 0.002, 310.0, 0.5, 11
+    eng.md_configure(integrator, dt, temp, gamma, MASS, seed)
+    eng.set_velocities_to_temperature(temp, seed)
+    x, v = case["x"].copy(), eng.get_velocities()
+    for step in range(3):
+        f = O.energy_forces(sysd, x)[1]
+        nrm = normals3(seed, 400, step, 1)
+        if integrator == "verlet":
+            v = v + dt * f / MASS
+            x = x + dt * v
+        elif integrator == "langevin":
+            a = np.exp(-gamma * dt)
+            v = a * v + (1 - a) / gamma * f / MASS + np.sqrt(KB * temp * (1 - a * a) / MASS) * nrm
+            x = x + dt * v
+        else:
+            dx = dt / (gamma * MASS) * f + np.sqrt(2 * KB * temp * dt / (gamma * MASS)) * nrm
+            x, v = x + dx, dx / dt
+    rep = eng.md_run(3)
+    assert rep["step"] == 3
+    # displacements are ~1e-4 nm per step; GPU forces carry the usual 1e-4 relative error
+    assert np.abs(eng.get_positions() - x).max() < 1e-7
+    assert np.abs(eng.get_velocities() - v).max() < 1e-4 * np.abs(v).max()
+    e_ref = O.energy_forces(sysd, eng.get_positions(), want_forces=False)[0].sum()
+    assert abs(rep["potential"] - e_ref) <= 1e-5 * abs(e_ref)
+    assert rep["kinetic"] == pytest.approx(0.5 * MASS * (eng.get_velocities() ** 2).sum(), rel=1e-12)
+    eng.close()
+
+
+def test_verlet_conserves_energy(built_lib):
+    case = make_case(1500, n_chrom=2, seed=9, terms=("EV", "SCB", "SC", "BOND", "LOOP", "ANGLE"))
+    eng = to_engine(case)
+    eng.minimize(10.0, 300)
+    eng.md_configure("verlet", 0.001, 310.0, 0.0, MASS, 3)
+    eng.set_velocities_to_temperature(310.0, 3)
+    tot = []
+    for _ in range(10):
+        rep = eng.md_run(100)
+        tot.append(rep["potential"] + rep["kinetic"])
+    kin = rep["kinetic"]
+    assert max(tot) - min(tot) < 0.05 * kin, (tot, kin)  # leapfrog: bounded fluctuation, no drift
+    eng.close()
+
+
+def test_langevin_thermostat_holds_the_temperature(built_lib):
+    case = make_case(3000, n_chrom=2, seed=10, terms=("EV", "SC", "BOND", "ANGLE"))
+    eng = to_engine(case)
+    eng.minimize(10.0, 200)
+    eng.md_configure("langevin", 0.001, 310.0, 20.0, MASS, 4)  # strong friction: equilibrates in ~0.1 ps
+    temps = [eng.md_run(200)["temperature"] for _ in range(10)]
+    assert abs(np.mean(temps[3:]) - 310.0) < 0.05 * 310.0, temps
+    eng.close()
+
+
+def test_driver_runs_md_and_writes_the_reference_outputs(built_lib, tmp_path):
+    from multimm_b200 import cif, run
+
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    ini = tmp_path / "c.ini"
+    out = tmp_path / "out"
+    ini.write_text(f"[Main]\nPLATFORM = B200\nN_BEADS = 3000\nLOOPS_PATH = {gold}/synthetic_loops.bedpe\n"
+                   f"OUT_PATH = {out}\nSAVE_PLOTS = False\nMIN_MAX_ITERATIONS = 200\nSIM_RUN_MD = True\n"
+                   "SIM_N_STEPS = 300\nSIM_SAMPLING_STEP = 100\nTRJ_FRAMES = 6\n")
+    assert run.main(["-c", str(ini)]) == 0
+    for rel in ("model/MultiMM_afterMD.cif", "md_frames/frame_1.cif", "md_frames/frame_3.cif",
+                "metadata/MultiMM_annealing.dcd", "metadata/md_thermodynamics.tsv"):
+        assert (out / rel).exists(), rel
+    frames = cif.read_dcd(str(out / "metadata/MultiMM_annealing.dcd"))
+    assert frames.shape == (6, 3000, 3)
+    last = cif.read_cif_coordinates(str(out / "model/MultiMM_afterMD.cif"), include_hetatm=True)
+    assert np.allclose(frames[-1], last, atol=2e-3)
+    rows = (out / "metadata/md_thermodynamics.tsv").read_text().strip().split("\n")
+    assert len(rows) == 4 and rows[0].startswith("step")
