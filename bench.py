@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — force evaluations per second of the genome-wide MultiMM model on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload gw|chrom|region]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload gw|chrom|region|stress] [--decompose]
 
 Metric (BASELINE.json: "genome-wide minimization wall-time; force evals/s; ..."): combined
 energy+force evaluations per second of the genome-wide system (N = 2e5 beads, flags of
@@ -20,6 +21,8 @@ files in the reference's formats -> loaders -> MultiMM.add_* -> engine (C-ABI).
            bounded sample of the same system.  OpenMM itself is not installable in this image.
 N > 1 (torchrun): one independent replica per GPU (ensemble members, seeds = rank), no data-path
 collective; value = evaluations of all ranks / max-over-ranks device time; scaling "weak".
+--decompose (N > 1): ONE system (use --workload stress, N = 2e6) whose pair work is shared by the
+ranks, one NCCL all-reduce of forces + energies per evaluation; scaling "strong".
 """
 from __future__ import annotations
 
