@@ -14,10 +14,11 @@
 //   k_cell_keys   (HBM: 16 B read + 8 B written per bead)   30-bit Morton key of the bead's cell
 //   CUB radix sort of (key, bead id) pairs, 30 key bits, stable => order is (key, id)
 //   k_cell_ranges (HBM: 8 + 16 B read, 16 + <=8 B written)  sorted float4 copy + [start, end) per cell
-//   k_pair_cells  one warp per cell: lanes hold up to 32 i-beads of the cell, all lanes walk the
-//                 same j-list (the 27 neighbouring cells, fixed order, broadcast loads), gather
-//                 formulation => fixed summation order, no atomics.  FP32 inside a neighbour cell,
-//                 FP64 across cells.  Every form of every term is supported (pairmath::pair_generic).
+//   k_pair_cells  one warp per 32 consecutive sorted beads, one bead per lane; every lane walks the 27
+//                 cells around its own cell in fixed order (neighbouring lanes share most
+//                 j-addresses), gather formulation => fixed summation order, no atomics.  FP32 inside
+//                 a neighbour cell, FP64 across cells.  Default forms specialised; every other form
+//                 of every term through pairmath::pair_generic.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "mmm_internal.cuh"
@@ -192,9 +193,8 @@ __device__ __forceinline__ bool pair_fast(const float4 pj, const IBead& b, const
   return live;
 }
 
-// One warp per 32 consecutive SORTED beads.  The beads of a warp lie in one or a few cells; the warp
-// takes its cells one at a time (lanes of other cells wait), so that all active lanes walk the same
-// j-list: the 27 neighbouring cells in fixed (z, y, x) order, broadcast loads.
+// One warp per 32 consecutive SORTED beads, one bead per lane, gather formulation (fixed summation
+// order per bead, no atomics).
 // EVP = 0: any functional form (pair_generic).
 template <int EVP, int GK>
 __global__ void __launch_bounds__(kCellWarps * 32) k_pair_cells(const CellArgs A) {
@@ -220,39 +220,42 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_pair_cells(const CellArgs A
   b.a_scb = e_scb_i * c.g_inv_rc2;
   b.a_cob = e_cob_i * c.g_inv_rc2;
 
-  unsigned todo = __ballot_sync(0xffffffffu, valid);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const uint32_t code = __shfl_sync(0xffffffffu, mykey, leader);
-    const bool mine = valid && mykey == code;
-    todo &= ~__ballot_sync(0xffffffffu, mine);
-    const int cx = (int)compact3(code), cy = (int)compact3(code >> 1), cz = (int)compact3(code >> 2);
-    for (int nz = cz - 1; nz <= cz + 1; ++nz) {
-      if (nz < 0 || nz >= g.dim) continue;
-      for (int ny = cy - 1; ny <= cy + 1; ++ny) {
-        if (ny < 0 || ny >= g.dim) continue;
-        for (int nx = cx - 1; nx <= cx + 1; ++nx) {
-          if (nx < 0 || nx >= g.dim) continue;
+  // Every lane walks the 27 cells around ITS OWN cell (the beads of a warp lie in one or a few
+  // adjacent cells, so most lanes share each j-address: the loads coalesce to a broadcast or two);
+  // the warp iterates to the longest of its lanes' ranges.  Fixed (z, y, x) order per bead.
+  const int cx = (int)compact3(mykey), cy = (int)compact3(mykey >> 1), cz = (int)compact3(mykey >> 2);
+  for (int dz = -1; dz <= 1; ++dz) {
+    for (int dy = -1; dy <= 1; ++dy) {
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+        const bool inside = valid && nx >= 0 && nx < g.dim && ny >= 0 && ny < g.dim && nz >= 0 && nz < g.dim;
+        int j0 = 0, j1 = 0;
+        if (inside) {
           const uint32_t nc = spread3((uint32_t)nx) | (spread3((uint32_t)ny) << 1) | (spread3((uint32_t)nz) << 2);
-          const int j0 = A.cstart[nc], j1 = A.cend[nc];
-          float fx = 0.f, fy = 0.f, fz = 0.f, e4[4] = {0.f, 0.f, 0.f, 0.f};
-          unsigned hits = 0;
-#pragma unroll 4
-          for (int j = j0; j < j1; ++j) {
-            const float4 pj = A.pos4s[j];
-            bool in;
-            if (EVP > 0) {
-              in = pair_fast<EVP, GK>(pj, b, c, mine && j != i, fx, fy, fz, e4);
-            } else {
-              const int oj = A.order[j];
-              in = pair_generic(pj, b, si, oi < oj, c, mine && j != i, fx, fy, fz, e4, c.cutoff2);
-            }
-            hits += in ? 1u : 0u;
-          }
-          cnt += hits;
-          dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
-          de[0] += (double)e4[0]; de[1] += (double)e4[1]; de[2] += (double)e4[2]; de[3] += (double)e4[3];
+          j0 = A.cstart[nc];
+          j1 = A.cend[nc];
         }
+        const int len = j1 - j0;
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        float fx = 0.f, fy = 0.f, fz = 0.f, e4[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned hits = 0;
+#pragma unroll 4
+        for (int t = 0; t < maxlen; ++t) {
+          const bool have = t < len;
+          const int j = have ? j0 + t : 0;
+          const float4 pj = A.pos4s[j];
+          bool in;
+          if (EVP > 0) {
+            in = pair_fast<EVP, GK>(pj, b, c, have && j != i, fx, fy, fz, e4);
+          } else {
+            const int oj = A.order[j];
+            in = pair_generic(pj, b, si, oi < oj, c, have && j != i, fx, fy, fz, e4, c.cutoff2);
+          }
+          hits += in ? 1u : 0u;
+        }
+        cnt += hits;
+        dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
+        de[0] += (double)e4[0]; de[1] += (double)e4[1]; de[2] += (double)e4[2]; de[3] += (double)e4[3];
       }
     }
   }

@@ -197,14 +197,17 @@ __device__ __forceinline__ void pairs16_packed(const JDup sjd, const int a, cons
       float r2a, r2b;
       unpk2(r2, r2a, r2b);
       const u64 r = pk2(fast_sqrt(r2a), fast_sqrt(r2b));
-      const u64 q = fma2(rs2, r, r2);
-      float qa, qb;
-      unpk2(q, qa, qb);
-      const u64 wr = pk2(fast_rcp(qa), fast_rcp(qb));  // w / r
-      const u64 w = mul2(r, wr);
-      const u64 wp = powi2<EVP>(w);
-      E.ev2 = add2(E.ev2, wp);
-      u64 fs = mul2(wp, wr);
+      u64 fs = pk2(0.0f, 0.0f);
+      if constexpr (EVP > 0) {
+        const u64 q = fma2(rs2, r, r2);
+        float qa, qb;
+        unpk2(q, qa, qb);
+        const u64 wr = pk2(fast_rcp(qa), fast_rcp(qb));  // w / r
+        const u64 w = mul2(r, wr);
+        const u64 wp = powi2<EVP>(w);
+        E.ev2 = add2(E.ev2, wp);
+        fs = mul2(wp, wr);
+      }
       if (CHBM == 1) {
         const u64 kc2 = pk2(c.chb_kc, c.chb_kc), one2 = pk2(1.0f, 1.0f), mone2 = pk2(-1.0f, -1.0f);
         const u64 t = fma2(kc2, r2, fma2(mone2, r, one2));  // kC r^2 + 1 - r
@@ -330,7 +333,7 @@ template <int EVP, int GK, int CHBM, bool SELF, bool WANT_J>
 __device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup sjd, const int a,
                                        const int b, IBeads& I, float (&out)[3], EAcc& E, const N3Consts& c,
                                        const int* __restrict__ si4, const int self_d) {
-  constexpr bool kPacked = N3_USE_F32X2 && EVP > 0 && GK == 0 && !SELF && CHBM <= 1;
+  constexpr bool kPacked = N3_USE_F32X2 && GK == 0 && !SELF && (EVP > 0 ? CHBM <= 1 : CHBM == 1);
   float s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;  // saved group (g even)
   float p0x = 0.f, p0y = 0.f, p0z = 0.f, p1x = 0.f, p1y = 0.f, p1z = 0.f;  // registers 0,1 after level "2"
 #pragma unroll 1
