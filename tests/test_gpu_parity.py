@@ -194,6 +194,42 @@ def test_sharded_pair_work_is_bit_identical(built_lib, world):
     assert np.array_equal(x1, x2)
 
 
+def test_full_size_properties(built_lib):
+    """BASELINE.json's genome-wide size (N = 2e5, 22 chromosomes, full term set), where the O(N^2) FP64
+    oracle takes minutes: size-independent properties instead.  (1) The two independent exact kernels
+    agree (Newton-3 / fixed-point vs gather / FP64 partials); (2) pair forces sum to zero (Newton's
+    third law) to FP32 accumulation accuracy; (3) energies do not
+    change under a rigid translation; (4) the oracle agrees on a 12 000-bead PREFIX of the same
+    system (bonded and pair terms restricted to the prefix)."""
+    n = 200000
+    case = make_case(n, n_chrom=22, seed=2024)
+    eng = to_engine(case)
+    e_n3, f_n3 = eng.energy_forces()
+    assert eng.pair_kernel_in_use == 2
+    eng.set_pair_kernel(1)
+    e_g, f_g = eng.energy_forces()
+    assert np.allclose(e_n3, e_g, rtol=2e-6, atol=1e-6)
+    assert force_rel_err(f_n3, f_g) <= F_TOL
+    eng.close()
+    # (2) pair terms only
+    pair_case = make_case(n, n_chrom=22, seed=2024, terms=("EV", "SCB", "CHB"))
+    eng = to_engine(pair_case)
+    e1, f = eng.energy_forces()
+    # the two sides of a pair are accumulated in different FP32 partial sums before the exact
+    # fixed-point reduction: the total cancels to FP32 accumulation accuracy
+    assert np.abs(f.sum(axis=0)).max() <= 1e-6 * np.abs(f).sum()
+    # (3)
+    eng.set_positions(pair_case["x"] + np.array([0.7, -1.3, 0.4]))
+    e2, _ = eng.energy_forces()
+    assert np.allclose(e1, e2, rtol=3e-6)
+    eng.close()
+    # (4) prefix against the oracle
+    m = 12000
+    sub = make_case(m, n_chrom=1, seed=1, terms=("EV", "SCB", "CHB"))
+    sub["x"], sub["s"], sub["chrom"] = pair_case["x"][:m].copy(), pair_case["s"][:m].copy(), pair_case["chrom"][:m].copy()
+    _check(sub)
+
+
 def test_translation_invariance(built_lib):
     case = make_case(4000, n_chrom=2, seed=10, terms=("EV", "SCB", "CHB", "BOND", "ANGLE", "LOOP"))
     eng = to_engine(case)
