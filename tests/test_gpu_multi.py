@@ -61,3 +61,30 @@ def test_two_gpus_one_system(built_lib):
         assert np.array_equal(e, e0) and np.array_equal(f, f0)
         assert rep["e_final"] == rep0["e_final"] and rep["evaluations"] == rep0["evaluations"]
         assert np.array_equal(x, x0)
+
+
+def test_ensemble_is_dealt_to_two_gpus(built_lib, tmp_path):
+    """run.py:471-485 semantics (replica i: SHUFFLING_SEED = i, run_<i>.tar.gz), replicas dealt
+    round-robin to two worker processes, one per GPU, no communication between them."""
+    import tarfile
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from multimm_b200 import run
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ini = tmp_path / "c.ini"
+    out = tmp_path / "ens"
+    ini.write_text(f"[Main]\nPLATFORM = B200\nN_BEADS = 4000\nLOOPS_PATH = {gold}/synthetic_loops.bedpe\n"
+                   f"COMPARTMENT_PATH = {gold}/synthetic_subcompartments.bed\nSCB_USE_SUBCOMPARTMENT_BLOCKS = True\n"
+                   f"OUT_PATH = {out}\nSAVE_PLOTS = False\nMIN_MAX_ITERATIONS = 60\nSHUFFLE_CHROMS = True\n"
+                   "GENERATE_ENSEMBLE = True\nN_ENSEMBLE = 5\n")
+    args, _ = run.get_config(["-c", str(ini)])
+    reports = run.run_ensemble(args, devices=[0, 1])
+    assert [r["replica"] for r in reports] == [0, 1, 2, 3, 4]
+    assert [r["device"] for r in reports] == [0, 1, 0, 1, 0]
+    for i in range(5):
+        assert tarfile.is_tarfile(str(out / f"run_{i}.tar.gz"))
+    assert len({round(r["e_final"], 3) for r in reports}) == 5
