@@ -12,7 +12,7 @@
 // twice (once from each side); energies are halved at the end.
 //
 // Tile classification (warp-uniform, from the 32-bead bounding boxes written by k_prepare):
-//   far   : box distance^2 >= rg2  -> Gaussian block terms are < 2^-40 of their prefactor and
+//   far   : box distance^2 >= rg2  -> Gaussian block terms are < 2^-26 of their prefactor and
 //           are skipped (below FP32 resolution of the accumulators); EV (+CHB) only.
 //   chrom : CHB needs work only where the chromosome ranges of the two tiles overlap; if both
 //           tiles are single-chromosome the per-pair comparison is dropped as well.
