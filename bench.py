@@ -324,10 +324,19 @@ def run_ours(opt):
         peak_tflops, mufu_tops = measure_fp32_peak(local)
         pair_ms_avg = pair_ms / K
         achieved = flops / (pair_ms_avg * 1e-3) / 1e12
+        traffic = None
+        try:  # DRAM bytes of one launch from the committed ncu --set full capture of this kernel
+            with open(os.path.join(ROOT, "profiles", "r01_pair_n3_traffic.json")) as fh:
+                tj = json.load(fh)
+            if eng.pair_kernel_in_use == 2 and opt.workload == "gw" and not decomposed:
+                traffic = tj["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         kernel_name = {1: "k_pair_exact (gather)", 2: "k_pair_n3 (Newton-3)", 3: "k_pair_cells"}.get(eng.pair_kernel_in_use, "none")
         roofline = dict(
             bound="fp32", kernel=kernel_name, achieved=achieved, peak=peak_tflops, unit="TFLOP/s",
-            frac=achieved / peak_tflops if peak_tflops > 0 else None, traffic=None,
+            frac=achieved / peak_tflops if peak_tflops > 0 else None, traffic=traffic,
+            traffic_unit="bytes of DRAM per launch (ncu capture under profiles/); the kernel is FMA-pipe bound",
             peak_source="FFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP32 entry); "
                         f"MUFU peak measured likewise: {mufu_tops:.2f} Tera-op/s",
             algorithmic_flops_per_launch=flops, unordered_pairs_per_launch=pairs,
