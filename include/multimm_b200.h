@@ -194,6 +194,11 @@ int mmm_get_velocities(mmm_handle h, double *v_out);
  * (one fused force evaluation + one integrator launch each), energies read once at the end. */
 int mmm_md_run(mmm_handle h, int64_t n_steps, mmm_md_report *out);
 
+/* ---- structure report (plots.py:630-829 analyze_structure) ------------------------------------- */
+/* Mean of the full N x N distance matrix at the current positions (np.mean(cdist(V, V)),
+ * plots.py:663-664) without materialising it. */
+int mmm_mean_pair_distance(mmm_handle h, double *mean_out);
+
 /* ---- one system on several GPUs of one box (exact mode only) -------------------------------- */
 /* The reference has no multi-GPU path (DeviceIndex is never set, model.py:862-876).  Here the
  * O(N^2) pair work of ONE system is dealt to `world` handles, one per GPU / process, each holding

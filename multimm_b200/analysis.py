@@ -1,0 +1,104 @@
+"""Structure report — the numeric part of the reference's ``analyze_structure``
+(src/multimm/plots.py:630-829), re-hosted without matplotlib: same quantities, same report text,
+the curves the reference only plots are saved as arrays.
+
+The one O(N^2) quantity (mean of the full distance matrix, plots.py:663-664) comes from the engine
+when one is passed (a tiled kernel that never materialises the matrix: the reference needs N^2 x 8
+bytes, 320 GB at N = 2e5) and from a blocked numpy loop otherwise.  The O(N x window) local-Rg loop
+(plots.py:712-720) is replaced by prefix sums, O(N).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def mean_pair_distance_host(V: np.ndarray, block: int = 2048) -> float:
+    n = len(V)
+    total = 0.0
+    for a in range(0, n, block):
+        d = V[a:a + block, None, :] - V[None, :, :]
+        total += float(np.sqrt((d * d).sum(axis=2)).sum())
+    return total / (float(n) * float(n))
+
+
+def local_rg(V: np.ndarray, window: int) -> np.ndarray:
+    """sqrt(mean |x - cm|^2) over each window [i, i + window), i in [0, N - window): prefix sums."""
+    n = len(V)
+    if n - window <= 0:
+        return np.zeros(0)
+    c1 = np.vstack([np.zeros((1, 3)), np.cumsum(V, axis=0)])
+    c2 = np.concatenate([[0.0], np.cumsum((V * V).sum(axis=1))])
+    i = np.arange(n - window)
+    s1 = c1[i + window] - c1[i]
+    s2 = c2[i + window] - c2[i]
+    var = s2 / window - (s1 * s1).sum(axis=1) / (window * window)
+    return np.sqrt(np.maximum(var, 0.0))
+
+
+def analyze_structure(V, save_path, name="structure", engine=None) -> dict:
+    V = np.asarray(V, dtype=np.float64)
+    V = V[np.isfinite(V).all(axis=1)]
+    n = len(V)
+    base = os.path.join(save_path, "analysis")
+    os.makedirs(base, exist_ok=True)
+
+    r_cm = np.mean(V, axis=0)
+    Vc = V - r_cm
+    rg = np.sqrt(np.mean(np.sum(Vc ** 2, axis=1)))
+    ree = np.linalg.norm(V[-1] - V[0])
+    if engine is not None:
+        engine.set_positions(V)
+        mean_dist = engine.mean_pair_distance()
+    else:
+        mean_dist = mean_pair_distance_host(V)
+    try:
+        from scipy.spatial import ConvexHull
+
+        volume = ConvexHull(V).volume
+    except Exception:
+        volume = np.nan
+    density = n / volume if volume > 0 else np.nan
+    G = np.dot(Vc.T, Vc) / n
+    eigvals = np.sort(np.linalg.eigvalsh(G))
+    l1, l2, l3 = eigvals
+    asphericity = l3 - 0.5 * (l1 + l2)
+    acylindricity = l2 - l1
+    bonds = np.linalg.norm(np.diff(V, axis=0), axis=1)
+    v1, v2 = V[1:-1] - V[:-2], V[2:] - V[1:-1]
+    cos_angles = np.sum(v1 * v2, axis=1) / (np.linalg.norm(v1, axis=1) * np.linalg.norm(v2, axis=1) + 1e-8)
+    angles = np.arccos(np.clip(cos_angles, -1, 1))
+    separations = np.arange(1, min(500, n // 2))
+    spatial = np.array([np.mean(np.linalg.norm(V[s:] - V[:n - s], axis=1)) for s in separations])
+    window = max(10, n // 100)
+    lrg = local_rg(V, window)
+
+    with open(os.path.join(base, f"{name}_report.txt"), "w") as f:
+        f.write("===== STRUCTURE ANALYSIS =====\n\n")
+        f.write(f"N beads: {n}\n\n")
+        f.write("---- Global ----\n")
+        f.write(f"Rg: {rg:.4f}\n")
+        f.write(f"Ree: {ree:.4f}\n")
+        f.write(f"Mean distance: {mean_dist:.4f}\n\n")
+        f.write("---- Volume ----\n")
+        f.write(f"Volume: {volume:.4f}\n")
+        f.write(f"Density: {density:.6f}\n\n")
+        f.write("---- Shape ----\n")
+        f.write(f"Eigenvalues: {eigvals}\n")
+        f.write(f"Asphericity: {asphericity:.6f}\n")
+        f.write(f"Acylindricity: {acylindricity:.6f}\n\n")
+        f.write("---- Local properties ----\n")
+        f.write(f"Mean bond length: {np.mean(bonds):.4f}\n")
+        f.write(f"Mean angle (rad): {np.mean(angles):.4f}\n\n")
+        f.write("Interpretation:\n")
+        f.write("Rg ~ size of polymer\n")
+        f.write("Distance vs separation → scaling law\n")
+        f.write("Angles → stiffness\n")
+        f.write("Local Rg → domain compaction\n")
+    # what the reference draws (plots.py:765-829) saved as data
+    np.savez_compressed(os.path.join(base, f"{name}_curves.npz"), bonds=bonds, angles=angles, separations=separations,
+                        spatial_dists=spatial, local_rg=lrg)
+    return dict(n=n, rg=rg, ree=ree, mean_dist=mean_dist, volume=volume, density=density, eigvals=eigvals,
+                asphericity=asphericity, acylindricity=acylindricity, mean_bond=float(np.mean(bonds)),
+                mean_angle=float(np.mean(angles)), separations=separations, spatial_dists=spatial, local_rg=lrg)

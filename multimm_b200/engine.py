@@ -164,6 +164,12 @@ class Engine:
         self._ck(self._lib.mmm_minimize(self._h, float(tol), int(max_iter), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in MinReport._fields_}
 
+    def mean_pair_distance(self) -> float:
+        """np.mean(cdist(V, V)) at the current positions, computed on the device."""
+        out = C.c_double()
+        self._ck(self._lib.mmm_mean_pair_distance(self._h, C.byref(out)))
+        return float(out.value)
+
     # -- MD relaxation ----------------------------------------------------------------------------
     def md_configure(self, integrator="langevin", dt_ps=0.001, temperature_k=310.0, friction_per_ps=0.5,
                      mass_amu=16427.889, seed=0):

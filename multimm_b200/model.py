@@ -18,7 +18,7 @@ import time
 
 import numpy as np
 
-from . import _lib, cif, loaders, structures
+from . import _lib, analysis, cif, loaders, structures
 from .engine import Engine
 from .units import Quantity
 
@@ -327,6 +327,23 @@ class MultiMM:
             cif.write_mmcif_chrom(10.0 * self.positions[self.chr_ends[k]:self.chr_ends[k + 1]],
                                   self.save_path + f"model/chromosomes/MultiMM_minimized_{name}.cif")
 
+    def make_reports(self):
+        """The numeric part of make_plots (model.py:1069-1213): for single-chromosome / region runs
+        the reference analyses the initial, minimised and post-MD structures (analyze_structure,
+        plots.py:630-829); genome-wide runs return before that step.  Figures are not drawn here."""
+        multi = self._whole and self.chrom_idxs is not None and len(self.chrom_idxs) > 1
+        if multi:
+            return
+        todo = [("initial_structure", "metadata/MultiMM_init.cif"), ("minimized_structure", "model/MultiMM_minimized.cif")]
+        if self.args.SIM_RUN_MD:
+            todo.append(("structure_afterMD", "model/MultiMM_afterMD.cif"))
+        x_now = self.engine.get_positions()
+        for name, rel in todo:
+            V = cif.read_cif_coordinates(self.save_path + rel, include_hetatm=False)  # get_coordinates_cif
+            eng = self.engine if len(V) == self.args.N_BEADS else None
+            analysis.analyze_structure(V, self.save_path, name=name, engine=eng)
+        self.engine.set_positions(x_now)
+
     def save_args_to_txt(self, filename):
         """utils.py:733-742."""
         with open(filename, "w") as f:
@@ -348,6 +365,8 @@ class MultiMM:
             self.save_chromosomes()
         if self.args.SIM_RUN_MD:
             self.run_md()
+        if self.args.SAVE_PLOTS:
+            self.make_reports()
         self.save_args_to_txt(self.args.OUT_PATH + "/metadata/parameters.txt")
         return self.report
 

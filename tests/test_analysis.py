@@ -1,0 +1,54 @@
+"""Structure report against the text the REFERENCE's analyze_structure wrote for the same inputs
+(tests/golden/make_golden_analysis.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from multimm_b200 import analysis
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["walk400", "helix250"])
+def test_report_is_identical_to_the_reference(tmp_path, name):
+    V = np.load(os.path.join(GOLD, f"analysis_{name}_input.npy"))
+    analysis.analyze_structure(V, str(tmp_path), name=name)
+    ours = (tmp_path / "analysis" / f"{name}_report.txt").read_text()
+    with open(os.path.join(GOLD, f"analysis_{name}_report.txt")) as f:
+        assert ours == f.read()
+
+
+def test_local_rg_prefix_sums_match_the_reference_loop():
+    rng = np.random.default_rng(3)
+    V = np.cumsum(rng.normal(size=(700, 3)), axis=0)
+    window = 10
+    ref = []
+    for i in range(len(V) - window):  # plots.py:715-718
+        chunk = V[i:i + window]
+        cm = np.mean(chunk, axis=0)
+        ref.append(np.sqrt(np.mean(np.sum((chunk - cm) ** 2, axis=1))))
+    assert np.allclose(analysis.local_rg(V, window), ref, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_device_mean_distance_matches_cdist(built_lib, tmp_path):
+    from scipy.spatial import distance
+
+    from multimm_b200.engine import Engine
+
+    rng = np.random.default_rng(5)
+    for n in (3, 257, 5000):
+        V = np.cumsum(rng.normal(0, 0.1, size=(n, 3)), axis=0)
+        eng = Engine(n)
+        eng.set_positions(V)
+        got = eng.mean_pair_distance()
+        assert got == pytest.approx(np.mean(distance.cdist(V, V)), rel=2e-6)
+        eng.close()
+    # the report through the engine is the same text
+    V = np.load(os.path.join(GOLD, "analysis_walk400_input.npy"))
+    eng = Engine(len(V))
+    analysis.analyze_structure(V, str(tmp_path), name="walk400", engine=eng)
+    eng.close()
+    with open(os.path.join(GOLD, "analysis_walk400_report.txt")) as f:
+        assert (tmp_path / "analysis" / "walk400_report.txt").read_text() == f.read()

@@ -49,9 +49,14 @@ def test_cli_region_run_other_start(built_lib, tmp_path):
     from multimm_b200 import run
 
     ini, out = _ini(tmp_path, N_BEADS=500, CHROM="chr1", LOC_START=10000000, LOC_END=60000000,
-                    INITIAL_STRUCTURE_TYPE="helix")
+                    INITIAL_STRUCTURE_TYPE="helix", SAVE_PLOTS=True)
     assert run.main(["-c", ini]) == 0
     assert os.path.exists(os.path.join(out, "model/MultiMM_minimized.cif"))
+    # SAVE_PLOTS: the structure reports of make_plots (numbers, no figures)
+    for name in ("initial_structure", "minimized_structure"):
+        rep = open(os.path.join(out, "analysis", f"{name}_report.txt")).read()
+        assert rep.startswith("===== STRUCTURE ANALYSIS =====") and "Mean distance:" in rep
+        assert os.path.exists(os.path.join(out, "analysis", f"{name}_curves.npz"))
 
 
 def test_cli_rejects_cpu_platform(built_lib, tmp_path):
