@@ -475,9 +475,34 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
       E.ev2 = E.chb2 = pk2(0.0f, 0.0f);
 
       if (!i_all_pad) {
+        // Classify the stage's 8 tiles at once: lane s < 8 classifies tile s against this warp's
+        // i-beads, the steps fetch their class with one shuffle.  Class: -1 nothing to do;
+        // bits 0-1 CHB mode (0 none, 1 every pair same-chromosome, 2 compare per pair); bit 2
+        // within the Gaussian range.
+        int my_class = -1;
+        if (lane < N3_STEPS) {
+          const TileInfo jt = s_jt[buf][lane];
+          if (jt.cmin < MMM_PAD_CHROM) {  // not padding only
+            int chb_mode = 0;
+            if (CHB) {
+              const bool overlap = !(ib.cmax < jt.cmin || jt.cmax < ib.cmin);
+              const bool uniform = (ib.cmin == ib.cmax) && (jt.cmin == jt.cmax);
+              chb_mode = overlap ? (uniform ? 1 : 2) : 0;
+            }
+            bool near = false;
+            if (GK != 0) {
+              const float ddx = fmaxf(0.0f, fmaxf(ib.lox - jt.hix, jt.lox - ib.hix));
+              const float ddy = fmaxf(0.0f, fmaxf(ib.loy - jt.hiy, jt.loy - ib.hiy));
+              const float ddz = fmaxf(0.0f, fmaxf(ib.loz - jt.hiz, jt.loz - ib.hiz));
+              near = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) < c.rg2;
+            }
+            my_class = chb_mode | (near ? 4 : 0);
+            if (EVP == 0 && chb_mode == 0) my_class = -1;  // CHB-only pass: nothing to do for this tile pair
+          }
+        }
         for (int step = 0; step < N3_STEPS; ++step) {
-          const TileInfo jt = s_jt[buf][step];
-          if (jt.cmin >= MMM_PAD_CHROM) continue;  // padding only
+          const int cls = __shfl_sync(0xffffffffu, my_class, step);
+          if (cls < 0) continue;
           const float4* sj = s_j[buf] + step * MMM_TILE;
           const JDup sjd = {s_jxy[buf] + step * MMM_TILE, s_jz[buf] + step * MMM_TILE};
           float fj[3];
@@ -486,21 +511,8 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
             step64<EVP, GK, CHB ? 2 : 0, true, false>(sj, sjd, a, b, I, fj, E, c, s_it + iw, self_d);
             continue;  // ordered pairs: the j side is somebody's i side in this same stage pair
           }
-          int chb_mode = 0;
-          if (CHB) {
-            const bool overlap = !(ib.cmax < jt.cmin || jt.cmax < ib.cmin);
-            const bool uniform = (ib.cmin == ib.cmax) && (jt.cmin == jt.cmax);
-            chb_mode = overlap ? (uniform ? 1 : 2) : 0;
-          }
-          bool near = false;
-          if (GK != 0) {
-            const float ddx = fmaxf(0.0f, fmaxf(ib.lox - jt.hix, jt.lox - ib.hix));
-            const float ddy = fmaxf(0.0f, fmaxf(ib.loy - jt.hiy, jt.loy - ib.hiy));
-            const float ddz = fmaxf(0.0f, fmaxf(ib.loz - jt.hiz, jt.loz - ib.hiz));
-            near = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) < c.rg2;
-          }
-          if (EVP == 0 && chb_mode == 0) continue;  // CHB-only pass: nothing to do for this tile pair
-          if (near) {
+          const int chb_mode = cls & 3;
+          if (cls & 4) {
             if (!CHB || chb_mode == 0) step64<EVP, GK, 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
             else if (chb_mode == 1) step64<EVP, GK, CHB ? 1 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
             else step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
