@@ -47,6 +47,10 @@ constexpr int N3_IB = 512;                 // i-beads per block
 constexpr int N3_JB = 256;                 // j-beads per stage
 constexpr int N3_STEPS = N3_JB / MMM_TILE; // 8
 constexpr double N3_FIXED = 16777216.0;    // 2^24
+#ifndef N3_GROUP_UNROLL
+#define N3_GROUP_UNROLL 2
+#endif
+constexpr int kGroupUnroll = N3_GROUP_UNROLL;
 #ifndef N3_USE_F32X2
 #define N3_USE_F32X2 1
 #endif
@@ -336,7 +340,7 @@ __device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup
   constexpr bool kPacked = N3_USE_F32X2 && GK == 0 && !SELF && (EVP > 0 ? CHBM <= 1 : CHBM == 1);
   float s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;  // saved group (g even)
   float p0x = 0.f, p0y = 0.f, p0z = 0.f, p1x = 0.f, p1y = 0.f, p1z = 0.f;  // registers 0,1 after level "2"
-#pragma unroll 1
+#pragma unroll kGroupUnroll
   for (int g = 0; g < 4; ++g) {
     float cx[2], cy[2], cz[2];
     if constexpr (kPacked) pairs16_packed<EVP, CHBM>(sjd, a, b, 2 * g, I, cx, cy, cz, E, c);
