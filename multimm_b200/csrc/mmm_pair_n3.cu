@@ -8,7 +8,8 @@
 //   i-block  = 512 consecutive beads, stationary in registers for a whole work item:
 //              warp w owns 64 of them, lane (a = lane >> 2, b = lane & 3) holds the 8 beads
 //              64 w + 8 a + {0..7}; the four b-lanes of a group hold the same beads.
-//   j-stage  = 256 consecutive beads in shared memory (float4 xyz + type bits), double buffered.
+//   j-stage  = 256 consecutive beads in shared memory (float4 xyz + type bits, and a negated,
+//              duplicated copy for the packed path), double buffered.
 //   step     = one tile of 32 j-beads: register ii of lane (a, b) meets j-bead 4 (jj ^ a) + b,
 //              jj = 0..7, so a lane evaluates an 8 x 8 rectangle = 64 pairs and a warp 64 x 32.
 //   item     = (i-block, run of <= cj j-stages), handed out by an atomic counter; only j-stages at
@@ -29,12 +30,20 @@
 //   energies: FP32 within a stage, FP64 across stages, one slot per item (fixed order).
 //
 // Tile classification is warp-uniform, from the 32-bead bounding boxes / chromosome ranges of
-// k_prepare: far tiles skip the Gaussians (< 2^-26 of their prefactor), CHB only where the
-// chromosome ranges overlap, per-pair chromosome compare only when a tile is not
-// single-chromosome.  The hot variant (far, no CHB) is 21 FP32-pipe/MUFU instructions per
-// unordered pair: 3 FADD, FMUL + 2 FFMA (r^2), MUFU.SQRT, FFMA (q = r^2 + r_s r), MUFU.RCP
-// (w/r), FMUL (w), 3 FMUL (w^6), FADD (energy), FMUL, 6 FFMA (both force accumulators).
-// Roofline: instruction issue (128 lanes/clk/SM); MUFU.SQRT/RCP co-issue (measured 32 lanes/clk/SM).
+// k_prepare (lane s classifies tile s of the stage, the steps fetch their class by shuffle): far
+// tiles skip the Gaussians (< 2^-26 of their prefactor), CHB only where the chromosome ranges
+// overlap, per-pair chromosome compare only when a tile is not single-chromosome.
+//
+// The hot variant (far, no CHB) per unordered pair: 3 add (dx,dy,dz), mul + 2 fma (r^2),
+// MUFU.SQRT, fma (q = r^2 + r_s r), MUFU.RCP (w/r), mul (w), 3 mul (w^6), add (energy), mul
+// (w^6 w/r), 6 fma (both force accumulators) = 19 FMA-pipe operations + 2 MUFU.  They are issued as
+// packed f32x2 instructions on two i-beads at a time (FFMA2 / FMUL2 / FADD2: 9.5 issue slots per
+// pair), which moves the bound from instruction issue to the FMA pipe: 19 cycles per warp-pair per
+// scheduler.  The 64 pairs of a step run as a rolled loop over 16-pair groups, unrolled by 2 (a
+// fully unrolled body was instruction-fetch bound); the stationary beads are loaded from
+// coordinate planes (d_soa) so that they arrive as aligned register pairs.
+// Measured (profiles/r01_pair_n3_*): the hot loop runs at ~78 % of that floor, the kernel at
+// 0.58-0.60 of the measured FFMA peak on SURVEY 8(d)'s algorithmic flops (28 flop per EV pair).
 #include <algorithm>
 
 #include "mmm_internal.cuh"
