@@ -9,18 +9,20 @@
 // bit-exact (tests/test_gpu_parity.py).  CHB's polynomial grows with r and cannot be truncated:
 // when CHB is on, an exact all-pairs pass restricted to CHB runs beside the cell-list pass.
 //
-// Per evaluation
+// Per evaluation (all hand-written; the sort is a counting sort by cell, which the cell structure
+// gives for free, followed by an id-rank inside each cell so that the order is exactly (key, id) —
+// the oracle's stable sort — whatever order the atomics landed in):
 //   k_cell_grid   (1 block)  bounding box of the real tiles -> origin, cell edge (>= rc), dim <= 64
-//   k_cell_keys   (HBM: 16 B read + 8 B written per bead)   30-bit Morton key of the bead's cell
-//   CUB radix sort of (key, bead id) pairs, 30 key bits, stable => order is (key, id)
-//   k_cell_ranges (HBM: 8 + 16 B read, 16 + <=8 B written)  sorted float4 copy + [start, end) per cell
+//   k_cell_keys   30-bit Morton key of the bead's cell + histogram (RED.ADD per bead)      16 B read,  4 B written per bead
+//   k_cell_scan   (1 block)  exclusive scan of the 8^bits cell counts in use -> [start, end) per cell
+//   k_cell_place  unstable placement: slot = start[key] + atomic cursor                    8 B written per bead
+//   k_cell_rank   rank of the bead's id inside its cell segment -> final slot; writes the sorted
+//                 keys, ids and the sorted float4 copy                                     16 B read, 24 B written per bead
 //   k_pair_cells  one warp per 32 consecutive sorted beads, one bead per lane; every lane walks the 27
 //                 cells around its own cell in fixed order (neighbouring lanes share most
 //                 j-addresses), gather formulation => fixed summation order, no atomics.  FP32 inside
 //                 a neighbour cell, FP64 across cells.  Default forms specialised; every other form
 //                 of every term through pairmath::pair_generic.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "mmm_internal.cuh"
 #include "mmm_pairmath.cuh"
 
@@ -102,27 +104,75 @@ __device__ __forceinline__ uint32_t cell_coord(float x, const CellGrid& g) {
 
 __global__ void __launch_bounds__(256) k_cell_keys(const float4* __restrict__ pos4, int64_t n,
                                                    const CellGrid* __restrict__ gp, uint32_t* __restrict__ keys,
-                                                   int* __restrict__ ids, const int* __restrict__ skip) {
+                                                   int* __restrict__ count, const int* __restrict__ skip) {
   if (skip && *skip) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const CellGrid g = *gp;
   const float4 p = pos4[i];
-  keys[i] = spread3(cell_coord(p.x, g)) | (spread3(cell_coord(p.y, g)) << 1) | (spread3(cell_coord(p.z, g)) << 2);
-  ids[i] = (int)i;
+  const uint32_t k = spread3(cell_coord(p.x, g)) | (spread3(cell_coord(p.y, g)) << 1) | (spread3(cell_coord(p.z, g)) << 2);
+  keys[i] = k;
+  atomicAdd(count + k, 1);
 }
 
-__global__ void __launch_bounds__(256) k_cell_ranges(const float4* __restrict__ pos4, int64_t n,
-                                                     const uint32_t* __restrict__ keys, const int* __restrict__ order,
-                                                     float4* __restrict__ pos4s, int* __restrict__ cstart,
-                                                     int* __restrict__ cend, const int* __restrict__ skip) {
+// Exclusive scan of the cell counts over the codes in use (8^bits <= kMaxCodes), one block of 1024
+// threads, a run of consecutive cells each.
+__global__ void __launch_bounds__(1024) k_cell_scan(const CellGrid* __restrict__ gp, const int* __restrict__ count,
+                                                    int* __restrict__ cstart, int* __restrict__ cend,
+                                                    const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ int s_sum[1024];
+  const int ncodes = 1 << (3 * gp->bits);
+  const int per = (ncodes + 1023) / 1024;
+  const int t = threadIdx.x;
+  const int lo = min(t * per, ncodes), hi = min(lo + per, ncodes);
+  int local = 0;
+  for (int idx = lo; idx < hi; ++idx) local += count[idx];
+  s_sum[t] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+    const int v = t >= o ? s_sum[t - o] : 0;
+    __syncthreads();
+    s_sum[t] += v;
+    __syncthreads();
+  }
+  int run = s_sum[t] - local;  // exclusive prefix of this thread's first cell
+  for (int idx = lo; idx < hi; ++idx) {
+    const int cnt = count[idx];
+    cstart[idx] = run;
+    run += cnt;
+    cend[idx] = run;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cell_place(int64_t n, const uint32_t* __restrict__ keys,
+                                                    const int* __restrict__ cstart, int* __restrict__ cursor,
+                                                    int* __restrict__ slot_id, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = keys[i];
+  slot_id[cstart[k] + atomicAdd(cursor + k, 1)] = (int)i;
+}
+
+// Final slot of bead i = start of its cell + number of beads of the same cell with a smaller id.
+__global__ void __launch_bounds__(256) k_cell_rank(const float4* __restrict__ pos4, int64_t n,
+                                                   const uint32_t* __restrict__ keys, const int* __restrict__ cstart,
+                                                   const int* __restrict__ cend, const int* __restrict__ slot_id,
+                                                   uint32_t* __restrict__ keys_sorted, int* __restrict__ order,
+                                                   float4* __restrict__ pos4s, const int* __restrict__ skip) {
   if (skip && *skip) return;
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  const uint32_t k = keys[s];
-  pos4s[s] = pos4[order[s]];
-  if (s == 0 || keys[s - 1] != k) cstart[k] = (int)s;
-  if (s == n - 1 || keys[s + 1] != k) cend[k] = (int)s + 1;
+  const int i = slot_id[s];
+  const uint32_t k = keys[i];
+  const int j0 = cstart[k], j1 = cend[k];
+  int rank = 0;
+  for (int j = j0; j < j1; ++j) rank += slot_id[j] < i ? 1 : 0;
+  const int dst = j0 + rank;
+  keys_sorted[dst] = k;
+  order[dst] = i;
+  pos4s[dst] = pos4[i];
 }
 
 struct CellArgs {
@@ -311,11 +361,9 @@ int mmm_cells_alloc(mmm_system* h) {
   MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_start, (size_t)2 * kMaxCodes * sizeof(int)));
   MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_grid, sizeof(CellGrid)));
   MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_npairs, (size_t)mmm_cells_energy_slots(h) * sizeof(unsigned long long)));
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->d_keys_tmp, h->d_keys, h->d_order_tmp, h->d_order, (int)n, 0, 30,
-                                  h->stream);
-  h->sort_tmp_bytes = bytes;
-  MMM_CUDA(h, cudaMalloc(&h->d_sort_tmp, bytes));
+  // per-cell histogram + placement cursor
+  h->sort_tmp_bytes = (size_t)2 * kMaxCodes * sizeof(int);
+  MMM_CUDA(h, cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
   return MMM_OK;
 }
 
@@ -336,14 +384,15 @@ int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
   if (collect) h->ev_cursor++;
   MMM_CUDA(h, cudaEventRecord(ea, h->stream));
 
-  MMM_CUDA(h, cudaMemsetAsync(h->d_cell_start, 0, (size_t)2 * kMaxCodes * sizeof(int), h->stream));
+  int* count = reinterpret_cast<int*>(h->d_sort_tmp);
+  int* cursor = count + kMaxCodes;
+  MMM_CUDA(h, cudaMemsetAsync(h->d_sort_tmp, 0, h->sort_tmp_bytes, h->stream));
   k_cell_grid<<<1, 256, 0, h->stream>>>(h->d_tiles, (int)h->ntiles, (float)h->cutoff, grid, d_skip);
-  k_cell_keys<<<blocks, 256, 0, h->stream>>>(h->d_pos4, h->n, grid, h->d_keys_tmp, h->d_order_tmp, d_skip);
-  size_t bytes = h->sort_tmp_bytes;
-  cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, bytes, h->d_keys_tmp, h->d_keys, h->d_order_tmp, h->d_order, n, 0, 30,
-                                  h->stream);
-  k_cell_ranges<<<blocks, 256, 0, h->stream>>>(h->d_pos4, h->n, h->d_keys, h->d_order, h->d_pos4_sorted, cstart, cend,
-                                               d_skip);
+  k_cell_keys<<<blocks, 256, 0, h->stream>>>(h->d_pos4, h->n, grid, h->d_keys_tmp, count, d_skip);
+  k_cell_scan<<<1, 1024, 0, h->stream>>>(grid, count, cstart, cend, d_skip);
+  k_cell_place<<<blocks, 256, 0, h->stream>>>(h->n, h->d_keys_tmp, cstart, cursor, h->d_order_tmp, d_skip);
+  k_cell_rank<<<blocks, 256, 0, h->stream>>>(h->d_pos4, h->n, h->d_keys_tmp, cstart, cend, h->d_order_tmp, h->d_keys,
+                                             h->d_order, h->d_pos4_sorted, d_skip);
   CellArgs A;
   A.pos4s = h->d_pos4_sorted;
   A.keys = h->d_keys;
@@ -367,7 +416,7 @@ int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
   } else {
     k_pair_cells<0, 0><<<cblocks, kCellWarps * 32, 0, h->stream>>>(A);
   }
-  h->launches += 5;  // + the radix-sort kernels of CUB (library), not counted
+  h->launches += 6;
   MMM_CUDA(h, cudaGetLastError());
   MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
