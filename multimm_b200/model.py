@@ -255,8 +255,12 @@ class MultiMM:
             # truncated at `coarse` gets close to a minimum at a fraction of the cost per
             # evaluation; the SAME stopping rule is then met on the exact all-pairs potential, so the
             # result satisfies exactly what minimizeEnergy() guarantees.
+            # A truncated potential is discontinuous at the cut-off, so this stage is not guaranteed
+            # to reach the gradient tolerance: it is bounded (MIN_COARSE_MAX_ITERATIONS, default
+            # 20 000); whatever it leaves undone the exact stage finishes.
+            cap = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
             self.engine.set_cutoff(coarse)
-            self.coarse_report = self.engine.minimize(tol=tol, max_iter=max_iter)
+            self.coarse_report = self.engine.minimize(tol=tol, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
             self.engine.set_cutoff(0.0)
         self.report = self.engine.minimize(tol=tol, max_iter=max_iter)
         self.positions = self.engine.get_positions()

@@ -289,15 +289,41 @@ def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -
              for dev, todo in plan.items() if todo]
     for p in procs:
         p.start()
-    results, errors = [], []
-    for _ in range(n):
-        kind, payload = queue.get()
-        (results if kind == "ok" else errors).append(payload)
-    for p in procs:
-        p.join()
+    try:
+        results, errors = collect_reports(procs, queue, n)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()  # exact processes we started
+            p.join()
     if errors:
         raise RuntimeError(f"{len(errors)} ensemble member(s) failed: {errors}")
     return sorted(results, key=lambda r: r["replica"])
+
+
+def collect_reports(procs, queue, n: int, poll_seconds: float = 2.0):
+    """Gather one report per replica from the workers.  A worker that dies without reporting
+    (killed, crashed inside native code) must not leave the parent waiting forever: when every worker
+    has exited and the queue is drained, the missing replicas are reported as failed."""
+    import queue as _q
+
+    results, errors = [], []
+    while len(results) + len(errors) < n:
+        try:
+            kind, payload = queue.get(timeout=poll_seconds)
+        except _q.Empty:
+            if any(p.is_alive() for p in procs):
+                continue
+            try:  # the workers are gone: one last look at what they left behind
+                kind, payload = queue.get(timeout=poll_seconds)
+            except _q.Empty:
+                seen = {r["replica"] for r in results} | {e["replica"] for e in errors}
+                codes = [p.exitcode for p in procs]
+                errors.extend(dict(replica=i, error=f"worker exited without a report (exit codes {codes})")
+                              for i in range(n) if i not in seen)
+                break
+        (results if kind == "ok" else errors).append(payload)
+    return results, errors
 
 
 def visible_devices(args) -> list[int]:

@@ -146,3 +146,69 @@ class TestEnsemblePlumbing:
     def test_ensemble_needs_a_count(self):
         with pytest.raises(ValueError):
             run.run_ensemble(make_config(GENERATE_ENSEMBLE=True), devices=[0])
+
+
+class _FakeProc:
+    def __init__(self, alive_polls, exitcode):
+        self.alive_polls, self.exitcode = alive_polls, exitcode
+
+    def is_alive(self):
+        self.alive_polls -= 1
+        return self.alive_polls >= 0
+
+
+class TestWorkerLiveness:
+    def test_dead_worker_does_not_hang_the_parent(self):
+        """One worker reported, the other was killed (e.g. inside native code) without a word."""
+        import queue as q
+
+        box = q.Queue()
+        box.put(("ok", dict(replica=0, device=0)))
+        procs = [_FakeProc(0, 0), _FakeProc(1, -9)]
+        results, errors = run.collect_reports(procs, box, 3, poll_seconds=0.05)
+        assert [r["replica"] for r in results] == [0]
+        assert sorted(e["replica"] for e in errors) == [1, 2]
+        assert "exited without a report" in errors[0]["error"] and "-9" in errors[0]["error"]
+
+    def test_all_reports_arrive(self):
+        import queue as q
+
+        box = q.Queue()
+        for i in range(4):
+            box.put(("ok" if i != 2 else "error", dict(replica=i, device=i % 2, error="boom")))
+        results, errors = run.collect_reports([_FakeProc(5, 0)], box, 4, poll_seconds=0.05)
+        assert len(results) == 3 and [e["replica"] for e in errors] == [2]
+
+
+def test_coarse_stage_is_bounded(tmp_path, monkeypatch):
+    """MIN_COARSE_CUTOFF: the cut-off stage never runs unbounded, the exact stage keeps the user's bound."""
+    from multimm_b200 import model
+
+    calls = []
+
+    class Eng:
+        def __init__(self, n, device=0):
+            self.n = n
+
+        def __getattr__(self, name):
+            def rec(*a, **k):
+                calls.append((name, a, k))
+                if name == "minimize":
+                    return dict(iterations=1, evaluations=2, e_initial=1.0, e_final=0.0, rms_force=1.0, wall_seconds=0.0,
+                                converged=1, ls_status=0)
+                if name == "get_positions":
+                    import numpy as np
+                    return np.zeros((self.n, 3))
+                if name == "hilbert_points":
+                    from multimm_b200 import structures
+                    return structures.hilbert_points_host(self.n, 8)
+            return rec
+
+    monkeypatch.setattr(model, "Engine", Eng)
+    m = model.MultiMM(make_config(PLATFORM="B200", N_BEADS=6000, OUT_PATH=str(tmp_path / "o"), SAVE_PLOTS=False,
+                                  MIN_COARSE_CUTOFF=0.5))
+    m.set_radiuses(); m.initialize_simulation(); m.add_forcefield(); m.min_energy()
+    seq = [(n, a, k) for n, a, k in calls if n in ("set_cutoff", "minimize")]
+    assert [n for n, _, _ in seq] == ["set_cutoff", "minimize", "set_cutoff", "minimize"]
+    assert seq[0][1] == (0.5,) and seq[2][1] == (0.0,)
+    assert seq[1][2]["max_iter"] == 20000 and seq[3][2]["max_iter"] == 0
