@@ -250,6 +250,10 @@ class MultiMM:
         coarse = float(getattr(a, "MIN_COARSE_CUTOFF", 0.0) or 0.0)
         final_cutoff = float(getattr(a, "PAIR_CUTOFF", 0.0) or 0.0)
         self.coarse_report = None
+        if final_cutoff > 0.0 and max_iter == 0:
+            # a truncated potential jumps at the cut-off: unlimited iterations could go on for ever
+            max_iter = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
+            logger.warning(f"PAIR_CUTOFF > 0 with unlimited iterations: bounded at {max_iter} L-BFGS iterations")
         if coarse > 0.0 and final_cutoff == 0.0:
             # opt-in two-stage minimisation (not in the reference): L-BFGS on the cell-list forces
             # truncated at `coarse` gets close to a minimum at a fraction of the cost per

@@ -145,3 +145,25 @@ def test_other_platforms_are_refused(tmp_path, monkeypatch):
     m.set_radiuses()
     with pytest.raises(Error, match="no CPU/OpenCL/Reference fallback"):
         m.initialize_simulation()
+
+
+def test_gene_level_region(tmp_path, monkeypatch):
+    """model.py:65-97: the gene table gives (chromosome, window, gene); gene_start / gene_end are the
+    gene's bead range inside the window.  The table itself (data/hg38_gtf_annotations.tsv, 4 MB) is
+    the reference's data file and is passed by path (GENE_TSV)."""
+    monkeypatch.setattr(model, "Engine", Recorder)
+    tsv = tmp_path / "genes.tsv"
+    tsv.write_text("gene_id\tgene_name\tchromosome\tstart\tend\n"
+                   "ENSG0001\tAAA\tchr1\t30000000\t30600000\n"
+                   "ENSG0002\tBBB\tchr2\t5000\t90000\n")
+    assert loaders.get_gene_region(str(tsv), gene_name="BBB", window_size=100000) == ("chr2", [0, 190000], [5000, 90000])
+    with pytest.raises(ValueError, match="not found"):
+        loaders.get_gene_region(str(tsv), gene_id="ENSG9999")
+    with pytest.raises(ValueError, match="must be provided"):
+        loaders.get_gene_region(str(tsv))
+    args = SimulationConfig(PLATFORM="B200", N_BEADS=1000, LOOPS_PATH=BEDPE, OUT_PATH=str(tmp_path / "g"), SAVE_PLOTS=False,
+                            MODELLING_LEVEL="gene", GENE_TSV=str(tsv), GENE_NAME="AAA", GENE_WINDOW=20_000_000)
+    m = model.MultiMM(args)
+    span = 40_600_000
+    assert m.gene_start == (20_000_000 * 1000) // span and m.gene_end == (20_600_000 * 1000) // span
+    assert list(m.chr_ends) == [0, 1000] and len(m.ms) > 0
