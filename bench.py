@@ -124,6 +124,20 @@ def oracle_system(m, n_sub: int):
     return sysd, x[sub].copy()
 
 
+def openmm_probe() -> str:
+    """is the real reference backend importable (also from a
+    driver-provided baseline/_ref)?  It is not in this image; the answer is recorded in the JSON line."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref_dir) and ref_dir not in sys.path:
+        sys.path.append(ref_dir)
+    try:
+        import openmm  # noqa: F401
+
+        return "importable (not used: the OpenMM arm of BASELINE.md section 3 is not written, it could never be run here)"
+    except Exception as e:  # ModuleNotFoundError in this image
+        return f"not importable ({type(e).__name__}): OpenMM-CPU and OpenMM-CUDA are unmeasured"
+
+
 def cpu_baseline(m, target_seconds: float = 12.0, reps: int = 1):
     """Oracle timed on all host cores on a bounded sample; extrapolated to the full system by
     pair count (the O(N^2) pair loop is > 99.9 % of the oracle's time)."""
@@ -150,7 +164,7 @@ def cpu_baseline(m, target_seconds: float = 12.0, reps: int = 1):
                 sample=f"CPU oracle (FP64 restatement of OpenMM Reference semantics, OpenMP x{cores}) on the first "
                        f"{n_sub} beads of the same system ({pairs_sub:.3g} pairs in {dt:.2f} s), scaled to "
                        f"{pairs_full:.3g} pairs; OpenMM itself is not installable here (no wheel, no network)",
-                pairs_per_s=pairs_sub / dt, sample_beads=n_sub, sample_seconds=dt)
+                pairs_per_s=pairs_sub / dt, sample_beads=n_sub, sample_seconds=dt, openmm=openmm_probe())
 
 
 class ClockSampler:
