@@ -57,8 +57,10 @@ const char* mmm_last_error(mmm_handle h) { return h ? h->err.c_str() : g_create_
 int mmm_create(int device, int64_t n_beads, mmm_handle* out) {
   if (!out) return mmm_fail(nullptr, MMM_ERR_ARG, "mmm_create: out is NULL");
   *out = nullptr;
-  if (n_beads < 2 || n_beads > (int64_t)1 << 27)
-    return mmm_fail(nullptr, MMM_ERR_ARG, "mmm_create: n_beads must be in [2, 2^27]");
+  // 2^24 = the number of points of the order-8 Hilbert curve the reference starts from
+  // (initial_structure_tools.py:157-166); it also keeps the work-item tables within 32-bit counts
+  if (n_beads < 2 || n_beads > (int64_t)1 << 24)
+    return mmm_fail(nullptr, MMM_ERR_ARG, "mmm_create: n_beads must be in [2, 2^24]");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
