@@ -108,3 +108,31 @@ def test_fixed_point_accumulation_is_order_independent():
     b = int(q[rng.permutation(len(q))].sum())
     assert a == b  # integer sums commute: the force does not depend on which CTA ran which item
     assert abs(a / 2.0 ** 24 - float(f.astype(np.float64).sum())) <= len(f) * 2.0 ** -25
+
+
+def test_counting_sort_by_cell_reproduces_the_stable_order():
+    """csrc/mmm_cells.cu: histogram -> exclusive scan -> unstable atomic placement -> id-rank inside
+    each cell.  Whatever order the atomics land in, the result is the (key, id) order of a stable
+    sort — the oracle's definition of the cell list."""
+    rng = np.random.default_rng(4)
+    n, ncodes = 5000, 512
+    keys = rng.integers(0, ncodes, size=n)
+    keys[rng.integers(0, n, size=200)] = 17  # a crowded cell
+    count = np.bincount(keys, minlength=ncodes)
+    cstart = np.concatenate([[0], np.cumsum(count)[:-1]])
+    cend = cstart + count
+    want = np.lexsort((np.arange(n), keys))  # stable sort by key, ties by id
+    for trial in range(3):
+        arrival = rng.permutation(n)  # the order in which the atomics happen to execute
+        cursor = np.zeros(ncodes, dtype=int)
+        slot_id = np.full(n, -1)
+        for i in arrival:
+            slot_id[cstart[keys[i]] + cursor[keys[i]]] = i
+            cursor[keys[i]] += 1
+        order = np.full(n, -1)
+        for s in range(n):
+            i = slot_id[s]
+            k = keys[i]
+            rank = int((slot_id[cstart[k]:cend[k]] < i).sum())
+            order[cstart[k] + rank] = i
+        assert np.array_equal(order, want)
