@@ -293,9 +293,10 @@ def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -
         results, errors = collect_reports(procs, queue, n)
     finally:
         for p in procs:
+            p.join(timeout=60)  # workers exit by themselves once their replicas are reported
             if p.is_alive():
                 p.terminate()  # exact processes we started
-            p.join()
+                p.join()
     if errors:
         raise RuntimeError(f"{len(errors)} ensemble member(s) failed: {errors}")
     return sorted(results, key=lambda r: r["replica"])
