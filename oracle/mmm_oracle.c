@@ -1,8 +1,9 @@
 /*
  * mmm_oracle.c — CPU oracle for the MultiMM hot path.  TEST INFRASTRUCTURE ONLY; see
- * mmm_oracle.h for who may load it.  PARITY UNPINNED (no OpenMM / hilbertcurve here, no
- * golden vectors in the reference's tests): pinned by closed-form known answers and finite
- * differences in tests/test_oracle.py.
+ * mmm_oracle.h for who may load it and for what pins it: the energy terms are held to the
+ * reference's own force-field builder (tests/test_forcefield_golden.py); OpenMM's evaluation
+ * engine, its minimiser and the hilbertcurve package are restated from documentation (parity
+ * unpinned there), with known answers and finite differences in tests/test_oracle.py.
  *
  * FP64 throughout, plain loops.  Each function cites the reference lines it restates
  * (paths relative to /root/reference/).  OpenMM conventions restated from its public

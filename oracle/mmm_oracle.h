@@ -4,12 +4,20 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this; the product (multimm_b200/) never does.
  *
- * PARITY UNPINNED: the arithmetic of this path lives in third-party OpenMM 8.5.1
- * (uv.lock:2462-2463) and hilbertcurve 2.0.5 (uv.lock:1129-1130); neither is installed
- * here, and the reference's tests hold no numeric golden vectors for the path
- * (tests/test_simulations.py asserts file existence only).  The oracle restates the
- * published semantics and is pinned by closed-form known answers, finite differences and
- * the reference's own input loaders (tests/golden/), not by OpenMM outputs.
+ * PARITY — what pins this oracle, and what does not.
+ * Pinned to the reference's own code, executed in the build container:
+ *   - the force field: tests/golden/make_golden_forcefield.py runs the UNMODIFIED add_* methods of
+ *     src/multimm/model.py against a recording stand-in for `openmm` and evaluates the Lepton
+ *     strings, parameters and bond / angle / loop lists they produce; tests/test_forcefield_golden.py
+ *     holds every per-term energy of this oracle to those values (1e-10), for every functional form;
+ *   - the input loaders, the start curves, the .cif / .psf writers and the structure report
+ *     (tests/golden/make_golden*.py).
+ * NOT pinned (restated from public documentation, marked [OpenMM] in the sources): OpenMM 8.5.1's
+ * own evaluation of those expressions and its LocalEnergyMinimizer / liblbfgs (uv.lock:2462-2463),
+ * and hilbertcurve 2.0.5 (uv.lock:1129-1130) — neither is installed or installable here, and the
+ * reference's tests hold no numeric vectors for the path (tests/test_simulations.py asserts file
+ * existence only).  For those parts: parity unpinned; closed-form known answers, finite
+ * differences and curve invariants in tests/test_oracle.py stand in.
  */
 #ifndef MMM_ORACLE_H
 #define MMM_ORACLE_H
