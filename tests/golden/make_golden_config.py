@@ -62,7 +62,7 @@ def plain(v):
 
 def load_reference():
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.lines", "matplotlib.colors", "pyvista", "seaborn",
-                 "mpl_toolkits", "mpl_toolkits.mplot3d", "pyBigWig", "hilbertcurve", "hilbertcurve.hilbertcurve", "tqdm",
+                 "mpl_toolkits", "mpl_toolkits.mplot3d", "pyBigWig", "hilbertcurve", "hilbertcurve.hilbertcurve",
                  "openmm", "openmm.app"):
         sys.modules[name] = MagicMock()
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]

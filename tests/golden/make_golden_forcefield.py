@@ -109,7 +109,7 @@ class System:
 
 def load_reference_model():
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.lines", "matplotlib.colors", "pyvista", "seaborn",
-                 "mpl_toolkits", "mpl_toolkits.mplot3d", "pyBigWig", "hilbertcurve", "hilbertcurve.hilbertcurve", "tqdm",
+                 "mpl_toolkits", "mpl_toolkits.mplot3d", "pyBigWig", "hilbertcurve", "hilbertcurve.hilbertcurve",
                  "openmm.app"):
         sys.modules[name] = MagicMock()
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
