@@ -111,8 +111,18 @@ def main():
     config, run, utils = load_reference()
     out = {name: outcome(config.SimulationConfig, run.ArgumentChanger, run.args_tests, utils.chrom_sizes, kw)
            for name, kw in CASES.items()}
+    # precedence defaults < ini < CLI through the reference's own get_config (run.py:349-395)
+    argv = ["-c", "tests/golden/sample_config.ini", "--n_beads", "4321", "--sc_use_spherical_container", "True",
+            "--modelling_level", "region", "--chrom", "chr2"]
+    old = sys.argv
+    sys.argv = ["MultiMM"] + argv
+    try:
+        cli = run.get_config()
+    finally:
+        sys.argv = old
     with open(os.path.join(HERE, "config_golden.json"), "w") as fh:
-        json.dump({"cases": CASES, "reference": out}, fh, indent=1, sort_keys=True)
+        json.dump({"cases": CASES, "reference": out, "cli_argv": argv,
+                   "cli_reference": {k: plain(v) for k, v in cli.model_dump().items()}}, fh, indent=1, sort_keys=True)
     for k, v in out.items():
         print(k, v["construct"], v.get("preset"), v.get("checks"))
 

@@ -66,6 +66,17 @@ def test_same_outcome_as_the_reference(name):
     assert got == ref["checks"], (name, got, ref["checks"])
 
 
+def test_cli_precedence_matches_the_reference_get_config():
+    """defaults < ini (all sections, keys case-folded) < CLI, then the presets: run.py:349-395."""
+    argv = [a if not a.endswith("sample_config.ini") else a for a in GOLD["cli_argv"]]
+    args, _ = run.get_config(argv)
+    ours = {k: plain(v) for k, v in args.model_dump().items()}
+    for field, want in GOLD["cli_reference"].items():
+        if field not in DIFFERENT:
+            assert same(want, ours[field]), (field, want, ours[field])
+    assert ours["N_BEADS"] == 5000 and ours["EV_POWER"] == 5.0  # the region preset wins over the CLI's n_beads
+
+
 def test_only_documented_extra_fields():
     """Fields this repo adds to the reference's set: the engine's own knobs, nothing else."""
     ref_fields = set(GOLD["reference"]["defaults"]["fields"])
