@@ -281,3 +281,47 @@ def test_cell_list_sorted_and_stable():
             out |= ((v >> b) & 1) << (3 * b)
         return out
     assert np.array_equal(keys, (spread(c[:, 0]) | (spread(c[:, 1]) << 1) | (spread(c[:, 2]) << 2)).astype(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------
+# Hilbert curve: the same algorithm in n dimensions (tests only)
+# ---------------------------------------------------------------------------------------------
+def _skilling_points(n_points, p, n):
+    """Skilling's transpose -> axes decode as hilbertcurve 2.x applies it, for any dimension n: the
+    distance is written as an n*p-bit string, axis a takes bits a, a+n, ...; Gray decode; undo the
+    excess work."""
+    out = []
+    for h in range(n_points):
+        bits = format(h, f"0{n * p}b")
+        x = [int(bits[a::n], 2) for a in range(n)]
+        z = 2 << (p - 1)
+        t = x[n - 1] >> 1
+        for i in range(n - 1, 0, -1):
+            x[i] ^= x[i - 1]
+        x[0] ^= t
+        q = 2
+        while q != z:
+            pm = q - 1
+            for i in range(n - 1, -1, -1):
+                if x[i] & q:
+                    x[0] ^= pm
+                else:
+                    t = (x[0] ^ x[i]) & pm
+                    x[0] ^= t
+                    x[i] ^= t
+            q <<= 1
+        out.append(x)
+    return out
+
+
+def test_hilbert_algorithm_reproduces_the_packages_documented_example():
+    """hilbertcurve's README example: HilbertCurve(p=1, n=2).points_from_distances(range(4)) is
+    [0,0], [0,1], [1,1], [1,0].  The package is not installable here; the n-dimensional form of the
+    restated algorithm reproduces that example, and its n = 3 case IS the oracle's generator."""
+    assert _skilling_points(4, 1, 2) == [[0, 0], [0, 1], [1, 1], [1, 0]]
+    for p in (1, 2, 3, 8):
+        m = min(512, 8 ** p)
+        assert np.array_equal(np.array(_skilling_points(m, p, 3)), O.hilbert_points(m, p))
+    # every order-p curve in 2-D is a Hamiltonian path of unit steps on the 2^p x 2^p grid
+    pts = np.array(_skilling_points(64, 3, 2))
+    assert len({tuple(q) for q in pts}) == 64 and (np.abs(np.diff(pts, axis=0)).sum(axis=1) == 1).all()
