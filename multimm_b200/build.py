@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",
     "-ccbin", "/usr/bin/g++",
+    "--threads", "0",  # the .cu files compile side by side (same SASS, half the wall time)
 ]
 
 
@@ -46,14 +47,22 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("MMM_EXTRA_NVCC_FLAGS", "").split(), "-o", LIB_PATH, *sources()]
+    # link into a private name and rename: a concurrent reader (another test worker, an ensemble
+    # worker) sees either the old library or the complete new one, never a half-written file
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("MMM_EXTRA_NVCC_FLAGS", "").split(), "-o", tmp, *sources()]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libmultimm_b200.so")
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed building libmultimm_b200.so")
+        os.replace(tmp, LIB_PATH)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB_PATH
 
 
