@@ -126,6 +126,26 @@ class Quantity:
             raise TypeError(f"incompatible units {self.unit.name} and {unit.name}")
         return self._value * self.unit.scale / unit.scale
 
+    # the arithmetic openmm.unit.Quantity offers and the reference uses on config values
+    # (model.py:678 forms 1.0 / r0 ** 2 from LE_HARMONIC_BOND_R0)
+    def __pow__(self, p):
+        return Quantity(self._value ** p, self.unit ** p)
+
+    def __mul__(self, other):
+        if isinstance(other, Quantity):
+            return Quantity(self._value * other._value, self.unit * other.unit)
+        return Quantity(self._value * other, self.unit)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        if isinstance(other, Quantity):
+            return Quantity(self._value / other._value, self.unit / other.unit)
+        return Quantity(self._value / other, self.unit)
+
+    def __rtruediv__(self, other):
+        return Quantity(other / self._value, self.unit ** -1)
+
     def __eq__(self, other):
         return isinstance(other, Quantity) and self.unit.dims == other.unit.dims and math.isclose(self.md, other.md)
 
