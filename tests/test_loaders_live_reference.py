@@ -4,6 +4,7 @@ reference checkout exists (the build container); the frozen cases of test_loader
 GPU box instead.  Integer outputs must be identical, distances equal to the last bit or two."""
 import importlib.util
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -17,10 +18,14 @@ pytestmark = pytest.mark.skipif(not os.path.exists(REF_UTILS), reason="reference
 
 @pytest.fixture(scope="module")
 def ref():
+    """The reference's utils.py; the stand-in modules planted for its imports are removed afterwards."""
+    before = set(sys.modules)
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
-    return mg.load_reference_utils()
+    yield mg.load_reference_utils()
+    for name in set(sys.modules) - before:
+        del sys.modules[name]
 
 
 def draw_case(seed):
