@@ -1,6 +1,7 @@
 """Config validation and CLI / ensemble host logic, modelled on the reference's
 tests/test_run_validation.py (12 tests, 4 classes) plus the ensemble plumbing the reference never tests."""
 import os
+import sys
 import tarfile
 import textwrap
 
@@ -10,6 +11,8 @@ from pydantic import ValidationError
 from multimm_b200 import run
 from multimm_b200.config import SimulationConfig
 from multimm_b200.run import args_tests
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 BEDPE = os.path.join(os.path.dirname(__file__), "golden", "synthetic_loops.bedpe")
 BED = os.path.join(os.path.dirname(__file__), "golden", "synthetic_subcompartments.bed")
@@ -212,3 +215,43 @@ def test_coarse_stage_is_bounded(tmp_path, monkeypatch):
     assert [n for n, _, _ in seq] == ["set_cutoff", "minimize", "set_cutoff", "minimize"]
     assert seq[0][1] == (0.5,) and seq[2][1] == (0.0,)
     assert seq[1][2]["max_iter"] == 20000 and seq[3][2]["max_iter"] == 0
+
+
+def test_ensemble_script_is_spawn_safe(monkeypatch):
+    """run_ensemble starts workers with `spawn`, which re-imports the main script in every worker: the
+    measuring script must do nothing at import (its unguarded first version left an 8-GPU run waiting
+    for workers that had died while bootstrapping, profiles/r01_ensemble.md)."""
+    import runpy
+
+    monkeypatch.setattr(sys, "argv", ["gpu_ensemble.py"])  # an unguarded body would fail on argv[1]
+    monkeypatch.chdir(ROOT)
+    runpy.run_path(os.path.join(ROOT, "scripts", "gpu_ensemble.py"), run_name="__mp_main__")
+
+
+def test_two_worker_ensemble_reports_instead_of_hanging(tmp_path):
+    """The whole spawn plumbing on a box without a GPU: two workers start, each replica fails inside
+    mmm_create (there is no CPU fallback), the failures travel back through the queue and the parent
+    raises — within seconds, and naming the device error."""
+    import subprocess
+
+    script = tmp_path / "ens.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r})
+        from multimm_b200 import run
+        from multimm_b200.config import SimulationConfig
+
+        if __name__ == "__main__":
+            args = SimulationConfig(PLATFORM="B200", N_BEADS=20000, LOOPS_PATH={os.path.join(ROOT, 'tests', 'golden', 'synthetic_loops.bedpe')!r},
+                                    OUT_PATH={str(tmp_path / 'out')!r}, SAVE_PLOTS=False, GENERATE_ENSEMBLE=True, N_ENSEMBLE=3)
+            try:
+                run.run_ensemble(args, devices=[0, 1])
+            except RuntimeError as e:
+                print("PARENT:", e)
+                sys.exit(7)
+        """))
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300,
+                         env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert res.returncode == 7, res.stdout + res.stderr
+    assert "3 ensemble member(s) failed" in res.stdout
+    assert "CUDA" in res.stdout
