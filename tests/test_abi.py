@@ -64,3 +64,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_pair_kernel_resources_allow_two_ctas_per_sm(built_lib):
+    """The Newton-3 kernel is designed for two resident 256-thread CTAs per SM:
+    <= 128 registers per thread, static shared memory within the 48 KB that needs no opt-in, and the
+    hot variant on packed f32x2 arithmetic.  A change that silently breaks one of these costs ~2x."""
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", built_lib], capture_output=True, text=True).stdout
+    rows = re.findall(r"Function (\S*k_pair_n3\S*):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)", out)
+    assert len(rows) >= 16, len(rows)
+    for name, reg, stack, shared in rows:
+        assert int(reg) <= 128, (name, reg)
+        assert int(shared) <= 48 * 1024, (name, shared)
+        assert int(stack) <= 64, (name, stack)  # a few spilled words in the rare variants, none in the hot one
+    gw = [n for n, *_ in rows if "k_pair_n3ILi6ELi1ELb1" in n]
+    assert len(gw) == 1
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", gw[0], built_lib], capture_output=True, text=True).stdout
+    assert sass.count("FFMA2") >= 100 and "FMUL2" in sass and "FADD2" in sass
+    assert "REDG.E.ADD.64" in sass  # the 64-bit fixed-point force accumulation
