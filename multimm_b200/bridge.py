@@ -6,6 +6,7 @@ CPU platform — there is none; and ensemble members of one call are dealt to th
 """
 from __future__ import annotations
 
+import contextlib
 import logging
 import os
 import subprocess
@@ -19,6 +20,43 @@ from .run import run_replica, visible_devices, write_config
 logger = logging.getLogger("multimm_b200")
 
 PLATFORM_ERRORS = ("Error initializing context", "CUDA error")
+ATTEMPTS = 3  # bridge.py:102-118
+
+
+def _metadata_dir(config) -> str:
+    meta = os.path.join(config.OUT_PATH, "metadata")
+    os.makedirs(meta, exist_ok=True)
+    return meta
+
+
+@contextlib.contextmanager
+def _run_log(path: str):
+    """The package logger also writes to <OUT_PATH>/metadata/output.log for the duration of a run."""
+    handler = logging.FileHandler(path, mode="w")
+    handler.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
+    level = logger.level
+    logger.addHandler(handler)
+    if level == logging.NOTSET or level > logging.INFO:
+        logger.setLevel(logging.INFO)
+    try:
+        yield
+    finally:
+        logger.removeHandler(handler)
+        handler.close()
+        logger.setLevel(level)
+
+
+def _with_retries(job, device: int):
+    """An engine failure is logged and the job repeated; the last failure propagates."""
+    for k in range(1, ATTEMPTS + 1):
+        try:
+            return job()
+        except Error as e:
+            kind = "platform" if any(s in str(e) for s in PLATFORM_ERRORS) else "engine"
+            logger.error(f"Simulation failed ({kind} error) on device {device}: {e}")
+            if k == ATTEMPTS:
+                raise
+            logger.warning(f"Attempt {k} failed, retrying...")
 
 
 class SimulationEngine:
@@ -38,48 +76,25 @@ class SimulationEngine:
         if fallback_to_cpu:
             raise Error(-3, "fallback_to_cpu=True: this engine has no CPU platform to fall back to")
         config = SimulationConfig(**config_params)
-        os.makedirs(config.OUT_PATH, exist_ok=True)
-        meta = os.path.join(config.OUT_PATH, "metadata")
-        os.makedirs(meta, exist_ok=True)
-        handler = logging.FileHandler(os.path.join(meta, "output.log"), mode="w")
-        handler.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
-        logger.addHandler(handler)
-        old_level = logger.level
-        if old_level == logging.NOTSET or old_level > logging.INFO:
-            logger.setLevel(logging.INFO)
-
-        def attempt(params: dict, seed: int, out_path: str, device: int):
-            for k in range(3):
-                try:
-                    return run_replica(params, seed, out_path, device, archive=False)
-                except Error as e:
-                    kind = "platform" if any(s in str(e) for s in PLATFORM_ERRORS) else "engine"
-                    logger.error(f"Simulation failed ({kind} error) on device {device}: {e}")
-                    if k == 2:
-                        raise
-                    logger.warning(f"Attempt {k + 1} failed, retrying...")
-
-        try:
+        meta = _metadata_dir(config)
+        params = config.model_dump()
+        devices = visible_devices(config)
+        with _run_log(os.path.join(meta, "output.log")):
             write_config(config)
-            params = config.model_dump()
-            devices = visible_devices(config)
             if config.GENERATE_ENSEMBLE and config.N_ENSEMBLE is not None:
-                base, seed0 = config.OUT_PATH, int(config.SHUFFLING_SEED)
-                for i in range(config.N_ENSEMBLE):  # bridge.py:96-100: seeds start+i, paths <base>_<i+1>
-                    attempt(params, seed0 + i, f"{base}_{i + 1}", devices[i % len(devices)])
+                # bridge.py:96-100: member i runs with seed start + i into <OUT_PATH>_<i+1>
+                jobs = [(int(config.SHUFFLING_SEED) + i, f"{config.OUT_PATH}_{i + 1}", devices[i % len(devices)])
+                        for i in range(config.N_ENSEMBLE)]
             else:
-                attempt(params, int(config.SHUFFLING_SEED), config.OUT_PATH, devices[0])
-        finally:
-            logger.removeHandler(handler)
-            handler.close()
-            logger.setLevel(old_level)
+                jobs = [(int(config.SHUFFLING_SEED), config.OUT_PATH, devices[0])]
+            for seed, out_path, device in jobs:
+                _with_retries(lambda: run_replica(params, seed, out_path, device, archive=False), device)
         return os.path.join(meta, "config_auto.ini")
 
     @classmethod
     def run_subprocess(cls, config_params: Dict[str, Any]) -> str:
         config = SimulationConfig(**config_params)
-        meta = os.path.join(config.OUT_PATH, "metadata")
-        os.makedirs(meta, exist_ok=True)
+        meta = _metadata_dir(config)
         config_path = write_config(config)
         with open(os.path.join(meta, "output.log"), "w") as log_file:
             subprocess.run([sys.executable, "-m", "multimm_b200.run", "-c", config_path], stdout=log_file,
