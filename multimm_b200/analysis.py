@@ -102,3 +102,38 @@ def analyze_structure(V, save_path, name="structure", engine=None) -> dict:
     return dict(n=n, rg=rg, ree=ree, mean_dist=mean_dist, volume=volume, density=density, eigvals=eigvals,
                 asphericity=asphericity, acylindricity=acylindricity, mean_bond=float(np.mean(bonds)),
                 mean_angle=float(np.mean(angles)), separations=separations, spatial_dists=spatial, local_rg=lrg)
+
+
+def contact_map(V, log_scale: bool = True, reorder_by_diagonal: bool = False, bins: int | None = None) -> np.ndarray:
+    """The matrix the reference's ``get_heatmap`` draws (plots.py:540-561): contact strength
+    1 / (d + 1)^(2/3) of every bead pair, log1p-transformed, optionally reordered by distance from
+    the centroid.  ``bins=None`` is that N x N matrix (the reference refuses it at N >= 5e4,
+    model.py:1095); ``bins=B`` returns the B x B matrix of block means over consecutive beads
+    instead, built block by block so that the N x N matrix never exists — the form in which a
+    genome-wide structure can still be looked at."""
+    V = np.asarray(V, dtype=np.float64)
+    n = len(V)
+    if reorder_by_diagonal:
+        V = V[np.argsort(np.linalg.norm(V - np.mean(V, axis=0), axis=1))]
+
+    def strength(a, b):
+        d = a[:, None, :] - b[None, :, :]
+        m = 1.0 / (np.sqrt((d * d).sum(axis=2)) + 1.0) ** (2.0 / 3.0)
+        return np.log1p(m) if log_scale else m
+
+    if bins is None:
+        out = np.empty((n, n))
+        for a in range(0, n, 1024):
+            out[a:a + 1024] = strength(V[a:a + 1024], V)
+        return out
+    bins = max(1, min(int(bins), n))  # no empty blocks
+    edges = np.linspace(0, n, bins + 1).astype(np.int64)
+    width = np.diff(edges)
+    out = np.zeros((bins, bins))
+    for p in range(bins):
+        a0, a1 = edges[p], edges[p + 1]
+        cols = np.zeros(n)
+        for a in range(a0, a1, 512):  # column sums of this block row, 512 beads at a time
+            cols += strength(V[a:min(a + 512, a1)], V).sum(axis=0)
+        out[p] = np.add.reduceat(cols, edges[:-1]) / ((a1 - a0) * width)
+    return out

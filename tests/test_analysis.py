@@ -52,3 +52,20 @@ def test_device_mean_distance_matches_cdist(built_lib, tmp_path):
     eng.close()
     with open(os.path.join(GOLD, "analysis_walk400_report.txt")) as f:
         assert (tmp_path / "analysis" / "walk400_report.txt").read_text() == f.read()
+
+
+def test_contact_map_block_means_never_need_the_full_matrix():
+    """contact_map(bins=B) equals the block means of the N x N matrix get_heatmap draws (plots.py:540-561)."""
+    rng = np.random.default_rng(1)
+    V = np.cumsum(rng.normal(size=(301, 3)), axis=0)
+    for kw in (dict(), dict(log_scale=False), dict(reorder_by_diagonal=True)):
+        full = analysis.contact_map(V, **kw)
+        assert full.shape == (301, 301) and np.allclose(full, full.T)
+        want_diag = np.log1p(1.0) if kw.get("log_scale", True) else 1.0
+        assert np.allclose(np.diag(full), want_diag)
+        for bins in (1, 9, 64, 301, 5000):
+            cg = analysis.contact_map(V, bins=bins, **kw)
+            b = min(bins, 301)
+            edges = np.linspace(0, 301, b + 1).astype(int)
+            ref = np.array([[full[edges[p]:edges[p + 1], edges[q]:edges[q + 1]].mean() for q in range(b)] for p in range(b)])
+            assert cg.shape == (b, b) and np.allclose(cg, ref, rtol=1e-12, atol=1e-14)

@@ -49,3 +49,18 @@ def test_report_text_equals_the_reference(plots, tmp_path, seed):
     want = (tmp_path / "ref" / "analysis" / f"{name}_report.txt").read_text()
     got = (tmp_path / "our" / "analysis" / f"{name}_report.txt").read_text()
     assert got == want
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_contact_map_equals_the_reference_heatmap(plots, tmp_path, seed):
+    """get_heatmap (plots.py:504-596) reads a CIF and returns the matrix it draws."""
+    from multimm_b200 import cif
+
+    V = draw(seed)[:300]
+    ends = np.array([0, len(V) // 3, len(V)])
+    path = str(tmp_path / "s.cif")
+    cif.write_mmcif(V, ends, path, hetatm_ends=bool(seed % 2), connections=False, decimals=4)
+    kw = dict(log_scale=bool(seed % 3), reorder_by_diagonal=bool(seed % 2 == 0))
+    want = plots.get_heatmap(path, viz=False, save=False, save_path=str(tmp_path / "plots"), **kw)
+    got = analysis.contact_map(cif.read_cif_coordinates(path, include_hetatm=False), **kw)
+    assert got.shape == want.shape and np.allclose(got, want, rtol=1e-12, atol=1e-14)
