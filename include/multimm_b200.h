@@ -109,7 +109,8 @@ typedef struct {
 /* ---- lifetime ------------------------------------------------------------------ */
 /* Replaces Platform.getPlatformByName + Simulation(...) (model.py:862-876). `device` is the
  * now-honoured DEVICE field (config.py:131). There is no CPU fallback: without a usable
- * sm_100 device this returns MMM_ERR_CUDA. */
+ * sm_100 device this returns MMM_ERR_CUDA.  2 <= n_beads <= 2^24, the number of points of the
+ * order-8 Hilbert curve the reference starts from (initial_structure_tools.py:157-166). */
 int mmm_create(int device, int64_t n_beads, mmm_handle *out);
 int mmm_destroy(mmm_handle h);
 /* Text of the last failure on `h` (or of the last failed mmm_create when h is NULL). */
