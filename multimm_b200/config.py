@@ -8,8 +8,10 @@
 * empty / "none" strings become None for Optional fields and for LOOPS_PATH, which makes a
   missing loops file a pydantic ValidationError (config.py:103-125, tests/test_run_validation.py:18-24).
 
-New meaning for two existing fields: PLATFORM accepts "B200" (and treats "CUDA" as B200); any
-other value is reported, not silently replaced — there is no CPU fallback.  DEVICE, which the
+New meaning for two existing fields: PLATFORM accepts "B200"; the OpenMM platform names (CUDA,
+OpenCL, CPU, Reference, HIP — every ini the reference ships says OpenCL) are taken as the
+preference they are in the reference (model.py:862-871) and run on the B200 engine with a logged
+warning; anything else is a ValueError.  There is no CPU path.  DEVICE, which the
 reference declares but never reads (config.py:131), selects the CUDA device index.
 """
 from __future__ import annotations
@@ -90,7 +92,9 @@ _FIELDS: dict[str, tuple[Any, Any]] = {
     "COMPARTMENT_NOISE_STD": (float, 0.0),
     "N_ENSEMBLE": (Optional[int], None),
     "DOWNSAMPLING_PROB": (float, 1.0),
-    "FORCEFIELD_PATH": (str, os.path.join(_PKG, "forcefields", "ff.xml")),
+    # accepted for config.ini compatibility and never read: the reference's ff.xml defines one atom
+    # type and no forces; the bead mass is loaders.BEAD_MASS
+    "FORCEFIELD_PATH": (str, ""),
     "N_BEADS": (int, 50000),
     "COMPARTMENT_PATH": (Optional[str], None),
     "LOOPS_PATH": (str, ""),

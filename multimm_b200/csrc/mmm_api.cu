@@ -231,6 +231,7 @@ int mmm_set_pair_term(mmm_handle h, int term, int form, const double* g, int ng)
       if (form >= 0) {
         REQUIRE(h, ng >= 4, "EV needs {epsilon, r_small, sigma, power}");
         p.ev_eps = (float)g[0]; p.ev_rs = (float)g[1]; p.ev_sigma = (float)g[2]; p.ev_power = (float)g[3];
+        memcpy(p.d_ev, g, 4 * sizeof(double));
       }
       break;
     case MMM_TERM_COB:
@@ -239,6 +240,7 @@ int mmm_set_pair_term(mmm_handle h, int term, int form, const double* g, int ng)
       if (form >= 0) {
         REQUIRE(h, ng >= 3, "COB needs {rc, Ea, Eb}");
         p.cob_rc = (float)g[0]; p.cob_ea = (float)g[1]; p.cob_eb = (float)g[2];
+        memcpy(p.d_cob, g, 3 * sizeof(double));
       }
       break;
     case MMM_TERM_SCB:
@@ -248,6 +250,7 @@ int mmm_set_pair_term(mmm_handle h, int term, int form, const double* g, int ng)
         REQUIRE(h, ng >= 5, "SCB needs {rsc, Ea1, Ea2, Eb1, Eb2}");
         p.scb_rc = (float)g[0];
         for (int q = 0; q < 4; ++q) p.scb_e[q] = (float)g[1 + q];
+        memcpy(p.d_scb, g, 5 * sizeof(double));
       }
       break;
     case MMM_TERM_CHB:
@@ -256,6 +259,7 @@ int mmm_set_pair_term(mmm_handle h, int term, int form, const double* g, int ng)
       if (form >= 0) {
         REQUIRE(h, ng >= 2, "CHB needs {k_C, dE}");
         p.chb_kc = (float)g[0]; p.chb_de = (float)g[1];
+        memcpy(p.d_chb, g, 2 * sizeof(double));
       }
       break;
     default:

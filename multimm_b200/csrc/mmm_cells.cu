@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_pair_cells(const CellArgs A
         const int len = j1 - j0;
         const int maxlen = __reduce_max_sync(0xffffffffu, len);
         float fx = 0.f, fy = 0.f, fz = 0.f, e4[4] = {0.f, 0.f, 0.f, 0.f};
+        double gx = 0.0, gy = 0.0, gz = 0.0, g4[4] = {0.0, 0.0, 0.0, 0.0};  // generic (FP64) path
         unsigned hits = 0;
 #pragma unroll 4
         for (int t = 0; t < maxlen; ++t) {
@@ -299,13 +300,18 @@ __global__ void __launch_bounds__(kCellWarps * 32) k_pair_cells(const CellArgs A
             in = pair_fast<EVP, GK>(pj, b, c, have && j != i, fx, fy, fz, e4);
           } else {
             const int oj = A.order[j];
-            in = pair_generic(pj, b, si, oi < oj, c, have && j != i, fx, fy, fz, e4, c.cutoff2);
+            in = pair_generic(pj, b, si, oi < oj, c, have && j != i, gx, gy, gz, g4, c.cutoff2);
           }
           hits += in ? 1u : 0u;
         }
         cnt += hits;
-        dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
-        de[0] += (double)e4[0]; de[1] += (double)e4[1]; de[2] += (double)e4[2]; de[3] += (double)e4[3];
+        if (EVP > 0) {
+          dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
+          de[0] += (double)e4[0]; de[1] += (double)e4[1]; de[2] += (double)e4[2]; de[3] += (double)e4[3];
+        } else {
+          dfx += gx; dfy += gy; dfz += gz;
+          de[0] += g4[0]; de[1] += g4[1]; de[2] += g4[2]; de[3] += g4[3];
+        }
       }
     }
   }

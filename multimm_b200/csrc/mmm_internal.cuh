@@ -55,6 +55,8 @@ struct PairParams {
   float g_inv_rc2;  // 1 / rc^2
   float rg2;        // squared range beyond which the Gaussian block terms are < 2^-26
   float cutoff2;    // cutoff^2 (cutoff mode) or 0
+  // the same globals in FP64, as handed to mmm_set_pair_term (generic any-form path)
+  double d_ev[4], d_cob[3], d_scb[5], d_chb[2];
 };
 
 struct ExternalParams {

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(MMM_IBLOCK) k_pair_exact(const PairArgs A) {
         de2 += (double)a.gscb;
         de3 += (double)a.echb;
       } else {
-        float fx = 0.f, fy = 0.f, fz = 0.f, e4[4] = {0.f, 0.f, 0.f, 0.f};
+        double fx = 0.0, fy = 0.0, fz = 0.0, e4[4] = {0.0, 0.0, 0.0, 0.0};
         for (int sub = 0; sub < nsub; ++sub) {
           const int jtile = jt + sub;
           const float4* sj = s_j + sub * MMM_TILE;
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(MMM_IBLOCK) k_pair_exact(const PairArgs A) {
             pair_generic(sj[jj], b, si, i < j, c, j != i, fx, fy, fz, e4);
           }
         }
-        dfx += (double)fx; dfy += (double)fy; dfz += (double)fz;
-        de0 += (double)e4[0]; de1 += (double)e4[1]; de2 += (double)e4[2]; de3 += (double)e4[3];
+        dfx += fx; dfy += fy; dfz += fz;
+        de0 += e4[0]; de1 += e4[1]; de2 += e4[2]; de3 += e4[3];
       }
     }
 

@@ -43,97 +43,98 @@ struct Acc {
 
 // Generic pair: any functional form, runtime switches, no tile skipping.  Used for the
 // non-default forms (model.py:205-211, 258-288, 338-378, 424-445) and non-integer EV powers.
+// The deltas are taken in FP32 from the centred FP32 coordinates (exactly what the specialised
+// kernels see, and the oracle's inclusion test in cut-off mode), everything after that is FP64
+// with the accurate libdevice functions: this is the slow path, it buys the north star's
+// 1e-5 / 1e-4 bars for every form instead of the 3e-5 / 2e-4 the lg2/ex2 formulation reached.
 // cut2 > 0: plain truncation, the pair counts iff r2 < cut2 with r2 = fma(dz,dz,fma(dy,dy,dx*dx))
-// on the centred FP32 coordinates (the oracle's pair_in_cut, bit for bit).  Returns whether the
-// pair contributed.
+// in FP32 (the oracle's pair_in_cut, bit for bit).  Returns whether the pair contributed.
 __device__ __forceinline__ bool pair_generic(const float4 pj, const IBead& b, const int si,
                                              const bool i_lower, const PairParams& c, bool live,
-                                             float& fx, float& fy, float& fz, float e4[4],
+                                             double& fx, double& fy, double& fz, double e4[4],
                                              const float cut2 = 0.0f) {
-  const float dx = b.x - pj.x, dy = b.y - pj.y, dz = b.z - pj.z;
-  float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-  if (cut2 > 0.0f && !(r2 < cut2)) live = false;
-  if (!live) r2 = 1.0f;
-  const float inv_r = fast_rsqrt(r2);
-  const float r = r2 * inv_r;
+  const float dxf = b.x - pj.x, dyf = b.y - pj.y, dzf = b.z - pj.z;
+  const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
+  if (cut2 > 0.0f && !(r2f < cut2)) live = false;
+  if (!live) return false;
+  const double dx = (double)dxf, dy = (double)dyf, dz = (double)dzf;
+  const double r2 = dx * dx + dy * dy + dz * dz;
+  const double r = sqrt(r2), inv_r = 1.0 / r;
   const int wj = __float_as_int(pj.w);
   const int sj = (wj & 7) - 2;
-  float dedr = 0.0f;  // dE/dr summed over terms
-  float e[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c.ev_form == MMM_EV_POWERLAW) {
-    const float w = fast_rcp(r + c.ev_rs);
-    const float en = c.ev_eps * fast_ex2(c.ev_power * fast_lg2(c.ev_sigma * w));
-    e[0] = en;
-    dedr -= c.ev_power * en * w;
-  } else if (c.ev_form == MMM_EV_GAUSSIAN_CORE) {
-    const float is2 = 1.0f / (c.ev_sigma * c.ev_sigma);
-    const float en = c.ev_eps * fast_ex2(-0.72134752f * r2 * is2);
-    e[0] = en;
+  double dedr = 0.0;  // dE/dr summed over terms
+  if (c.ev_form == MMM_EV_POWERLAW) {  // model.py:199
+    const double w = 1.0 / (r + c.d_ev[1]);
+    const double en = c.d_ev[0] * pow(c.d_ev[2] * w, c.d_ev[3]);
+    e4[0] += en;
+    dedr -= c.d_ev[3] * en * w;
+  } else if (c.ev_form == MMM_EV_GAUSSIAN_CORE) {  // model.py:209
+    const double is2 = 1.0 / (c.d_ev[2] * c.d_ev[2]);
+    const double en = c.d_ev[0] * exp(-0.5 * r2 * is2);
+    e4[0] += en;
     dedr -= en * r * is2;
   }
   if (c.cob_form >= 0) {
     const bool ai = si > 0, bi = si < 0, aj = sj > 0, bj = sj < 0;
-    float E;
+    double E;
     if (c.cob_form == MMM_BLOCK_YUKAWA) {
       // model.py:262-266 uses s1 on both factors; particle 1 is the lower index [OpenMM]
       const int s1 = i_lower ? si : sj;
-      E = s1 > 0 ? c.cob_ea : (s1 < 0 ? c.cob_eb : 0.0f);
+      E = s1 > 0 ? c.d_cob[1] : (s1 < 0 ? c.d_cob[2] : 0.0);
     } else {
-      E = (ai && aj) ? c.cob_ea : ((bi && bj) ? c.cob_eb : 0.0f);
+      E = (ai && aj) ? c.d_cob[1] : ((bi && bj) ? c.d_cob[2] : 0.0);
     }
-    if (c.cob_form == MMM_BLOCK_GAUSSIAN) {
-      const float irc2 = 1.0f / (c.cob_rc * c.cob_rc);
-      const float g = fast_ex2(-0.72134752f * r2 * irc2);
-      e[1] = -E * g;
+    if (c.cob_form == MMM_BLOCK_GAUSSIAN) {  // model.py:246-250
+      const double irc2 = 1.0 / (c.d_cob[0] * c.d_cob[0]);
+      const double g = exp(-0.5 * r2 * irc2);
+      e4[1] -= E * g;
       dedr += E * g * r * irc2;
     } else if (c.cob_form == MMM_BLOCK_YUKAWA) {
-      const float il = 1.0f / c.cob_rc;
-      const float g = fast_ex2(-1.44269504f * r * il);
-      e[1] = -E * g * inv_r;
+      const double il = 1.0 / c.d_cob[0];
+      const double g = exp(-r * il);
+      e4[1] -= E * g * inv_r;
       dedr += E * g * (il * inv_r + inv_r * inv_r);
-    } else {
-      e[1] = (c.cob_rc - r >= 0.0f) ? -E : 0.0f;
+    } else {  // model.py:279-283: -E step(rc - r), no force
+      e4[1] += (c.d_cob[0] - r >= 0.0) ? -E : 0.0;
     }
   }
   if (c.scb_form >= 0) {
-    float E = 0.0f;
-    if (si == sj && si != 0) E = c.scb_e[si == 2 ? 0 : (si == 1 ? 1 : (si == -1 ? 2 : 3))];
-    if (c.scb_form == MMM_BLOCK_GAUSSIAN) {
-      const float irc2 = 1.0f / (c.scb_rc * c.scb_rc);
-      const float g = fast_ex2(-0.72134752f * r2 * irc2);
-      e[2] = -E * g;
+    double E = 0.0;
+    if (si == sj && si != 0) E = c.d_scb[si == 2 ? 1 : (si == 1 ? 2 : (si == -1 ? 3 : 4))];
+    if (c.scb_form == MMM_BLOCK_GAUSSIAN) {  // model.py:322-328
+      const double irc2 = 1.0 / (c.d_scb[0] * c.d_scb[0]);
+      const double g = exp(-0.5 * r2 * irc2);
+      e4[2] -= E * g;
       dedr += E * g * r * irc2;
-    } else if (c.scb_form == MMM_BLOCK_YUKAWA) {
-      const float il = 1.0f / c.scb_rc;
-      const float g = fast_ex2(-1.44269504f * r * il);
-      e[2] = -E * g * inv_r;
+    } else if (c.scb_form == MMM_BLOCK_YUKAWA) {  // model.py:342-348
+      const double il = 1.0 / c.d_scb[0];
+      const double g = exp(-r * il);
+      e4[2] -= E * g * inv_r;
       dedr += E * g * (il * inv_r + inv_r * inv_r);
-    } else {
-      e[2] = (c.scb_rc - r >= 0.0f) ? -E : 0.0f;
+    } else {  // model.py:363-369
+      e4[2] += (c.d_scb[0] - r >= 0.0) ? -E : 0.0;
     }
   }
   if (c.chb_form >= 0 && ((b.w ^ wj) & 0xFFFF00) == 0) {
-    if (c.chb_form == MMM_CHB_POLYNOMIAL) {
-      e[3] = c.chb_de * r2 * fmaf(c.chb_kc, r2, 1.0f - r);
-      dedr += c.chb_de * r * fmaf(-3.0f, r, fmaf(4.0f * c.chb_kc, r2, 2.0f));
-    } else if (c.chb_form == MMM_CHB_GAUSSIAN) {
-      const float g = fast_ex2(-1.44269504f * c.chb_kc * r2);
-      e[3] = -c.chb_de * g;
-      dedr += 2.0f * c.chb_kc * r * c.chb_de * g;
-    } else {
-      const float q = fast_rcp(fmaf(c.chb_kc, r2, 1.0f));
-      e[3] = -c.chb_de * q;
-      dedr += c.chb_de * q * q * 2.0f * c.chb_kc * r;
+    const double kc = c.d_chb[0], de = c.d_chb[1];
+    if (c.chb_form == MMM_CHB_POLYNOMIAL) {  // model.py:416-419
+      e4[3] += de * r2 * (kc * r2 + 1.0 - r);
+      dedr += de * r * (4.0 * kc * r2 - 3.0 * r + 2.0);
+    } else if (c.chb_form == MMM_CHB_GAUSSIAN) {  // model.py:428-431
+      const double g = exp(-kc * r2);
+      e4[3] -= de * g;
+      dedr += 2.0 * kc * r * de * g;
+    } else {  // model.py:440-443
+      const double q = 1.0 / (kc * r2 + 1.0);
+      e4[3] -= de * q;
+      dedr += de * q * q * 2.0 * kc * r;
     }
   }
-  if (live) {
-    const float fs = -dedr * inv_r;
-    fx = fmaf(fs, dx, fx);
-    fy = fmaf(fs, dy, fy);
-    fz = fmaf(fs, dz, fz);
-    e4[0] += e[0]; e4[1] += e[1]; e4[2] += e[2]; e4[3] += e[3];
-  }
-  return live;
+  const double fs = -dedr * inv_r;
+  fx += fs * dx;
+  fy += fs * dy;
+  fz += fs * dz;
+  return true;
 }
 
 }  // namespace pairmath

@@ -50,6 +50,19 @@ def backbone_angles(n: int, chr_ends) -> np.ndarray:
     return i[~np.isin(i, ce) & ~np.isin(i, ce - 1)].astype(np.int32)
 
 
+OPENMM_PLATFORMS = ("CUDA", "OPENCL", "CPU", "REFERENCE", "HIP")
+
+
+def resolve_platform(name) -> str:
+    """"B200", or an OpenMM platform name (taken as a preference, like model.py:862-871) -> "B200";
+    anything else is a ValueError.  Called by run.args_tests too, so that a bad value fails before any I/O."""
+    p = str(name).strip().upper()
+    if p == "B200" or p in OPENMM_PLATFORMS:
+        return "B200"
+    raise ValueError(f"PLATFORM={name!r} is neither B200 nor an OpenMM platform name "
+                     f"({', '.join(OPENMM_PLATFORMS)}); this engine runs on a B200 only")
+
+
 class MultiMM:
     def __init__(self, args, device: int | None = None):
         self.args = args
@@ -62,6 +75,12 @@ class MultiMM:
             device = int(args.DEVICE) if str(getattr(args, "DEVICE", "")).strip().isdigit() else 0
         self.device = device
 
+        if str(args.MODELLING_LEVEL or "").lower() == "gene" and not _is_empty(args.GENE_TSV) \
+                and not os.path.exists(args.GENE_TSV):
+            # before the output tree is made or any file is parsed (upstream ships the table as package data)
+            raise ValueError(f"MODELLING_LEVEL=gene needs the gene annotation table, but GENE_TSV={args.GENE_TSV!r} "
+                             "does not exist. The 4 MB hg38 table is not shipped with this package: point GENE_TSV "
+                             "at MultiMM's src/multimm/data/hg38_gtf_annotations.tsv (any TSV with its columns).")
         # output tree (model.py:46-55)
         self.save_path = args.OUT_PATH + "/"
         for sub in ("md_frames", "plots", "metadata", "model"):
@@ -127,10 +146,13 @@ class MultiMM:
     def initialize_simulation(self):
         """model.py:722-810: start structure -> init CIF -> positions (nm) -> mass centre -> system."""
         a = self.args
-        platform = str(a.PLATFORM).upper()
-        if platform not in ("B200", "CUDA"):
-            raise _lib.Error(-3, f"PLATFORM={a.PLATFORM!r}: this engine runs on a B200 only (use B200 or CUDA); "
-                                 "there is no CPU/OpenCL/Reference fallback")
+        # PLATFORM is a preference in the reference (model.py:862-871 falls back when the named
+        # platform is unavailable); every config.ini it ships says OpenCL, its default is CPU.  Here
+        # every OpenMM platform name maps to the one backend there is; nothing ever runs on the CPU.
+        platform = resolve_platform(a.PLATFORM)
+        if platform != str(a.PLATFORM):
+            logger.warning(f"PLATFORM={a.PLATFORM!r} is an OpenMM platform name; running on the B200 engine "
+                           "(the only backend; there is no CPU/OpenCL/Reference path)")
         t0 = time.time()
         self.engine = Engine(a.N_BEADS, device=self.device)
         init_cif = self.save_path + "metadata/MultiMM_init.cif"

@@ -158,6 +158,17 @@ def args_tests(args):
     if args.CHB_USE_CHROMOSOMAL_BLOCKS:
         logger.warning("Chromosomal block forces are enabled. These are approximate.")
 
+    # checks the reference makes later (or never): here they fail before any I/O or GPU work
+    from . import _lib
+    from .model import resolve_platform
+
+    resolve_platform(args.PLATFORM)  # ValueError for anything that is neither B200 nor an OpenMM platform name
+    if args.SIM_RUN_MD and str(args.SIM_INTEGRATOR_TYPE).lower() not in _lib.MD_INTEGRATORS:
+        # the reference builds its integrator in initialize_simulation (model.py:768-808); a config
+        # that asks for one this engine does not have must not run a whole minimisation first
+        raise ValueError(f"SIM_INTEGRATOR_TYPE={args.SIM_INTEGRATOR_TYPE!r} is not available "
+                         f"(supported: {', '.join(_lib.MD_INTEGRATORS)})")
+
 
 def read_ini(path: str) -> dict:
     """Flat {UPPER_NAME: value} over all sections, DEFAULT last (run.py:334-346, 372-377)."""

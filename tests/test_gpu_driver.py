@@ -59,11 +59,17 @@ def test_cli_region_run_other_start(built_lib, tmp_path):
         assert os.path.exists(os.path.join(out, "analysis", f"{name}_curves.npz"))
 
 
-def test_cli_rejects_cpu_platform(built_lib, tmp_path):
+def test_cli_platform_names(built_lib, tmp_path):
+    """An ini written for the reference (PLATFORM = OpenCL / CPU) runs here, on the GPU; a name that is
+    no platform at all is refused before any work is done."""
     from multimm_b200 import run
 
-    ini, out = _ini(tmp_path, PLATFORM="CPU")
-    assert run.main(["-c", ini]) == 1  # no CPU fallback: reported, not silently replaced
+    ini, out = _ini(tmp_path, PLATFORM="TPU")
+    assert run.main(["-c", ini]) == 1
+    assert not os.path.exists(os.path.join(out, "model", "MultiMM_minimized.cif"))
+    ini, out = _ini(tmp_path, PLATFORM="OpenCL", MIN_MAX_ITERATIONS=20)
+    assert run.main(["-c", ini]) == 0
+    assert os.path.exists(os.path.join(out, "model", "MultiMM_minimized.cif"))
 
 
 def test_ensemble_members_differ_and_are_archived(built_lib, tmp_path):

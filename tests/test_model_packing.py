@@ -136,14 +136,23 @@ def test_compartment_forces_need_a_compartment_file(tmp_path, monkeypatch):
         m.add_forcefield()
 
 
-def test_other_platforms_are_refused(tmp_path, monkeypatch):
+def test_openmm_platform_names_run_on_the_engine(tmp_path, monkeypatch, caplog):
+    """Every ini the reference ships says PLATFORM = OpenCL and its default is CPU: those names are a
+    preference (model.py:862-871), not a request for a CPU path; unknown names are refused."""
     monkeypatch.setattr(model, "Engine", Recorder)
-    from multimm_b200 import Error
-
-    args = SimulationConfig(PLATFORM="OpenCL", N_BEADS=6000, LOOPS_PATH=BEDPE, OUT_PATH=str(tmp_path / "r"), SAVE_PLOTS=False)
+    for name in ("OpenCL", "CPU", "CUDA", "Reference", "B200"):
+        args = SimulationConfig(PLATFORM=name, N_BEADS=6000, LOOPS_PATH=BEDPE, OUT_PATH=str(tmp_path / name), SAVE_PLOTS=False)
+        m = model.MultiMM(args)
+        m.set_radiuses()
+        with caplog.at_level("WARNING"):
+            caplog.clear()
+            m.initialize_simulation()
+        assert isinstance(m.engine, Recorder)
+        assert (name == "B200") == (not any("OpenMM platform name" in r.message for r in caplog.records))
+    args = SimulationConfig(PLATFORM="TPU", N_BEADS=6000, LOOPS_PATH=BEDPE, OUT_PATH=str(tmp_path / "t"), SAVE_PLOTS=False)
     m = model.MultiMM(args)
     m.set_radiuses()
-    with pytest.raises(Error, match="no CPU/OpenCL/Reference fallback"):
+    with pytest.raises(ValueError, match="B200 only"):
         m.initialize_simulation()
 
 
@@ -167,3 +176,15 @@ def test_gene_level_region(tmp_path, monkeypatch):
     span = 40_600_000
     assert m.gene_start == (20_000_000 * 1000) // span and m.gene_end == (20_600_000 * 1000) // span
     assert list(m.chr_ends) == [0, 1000] and len(m.ms) > 0
+
+
+def test_gene_level_without_the_table_fails_early(tmp_path, monkeypatch):
+    """The default GENE_TSV points at package data this repo does not ship: a gene-level run says so
+    before it creates the output tree or parses anything (it used to die inside pandas)."""
+    monkeypatch.setattr(model, "Engine", Recorder)
+    out = tmp_path / "g2"
+    args = SimulationConfig(PLATFORM="B200", N_BEADS=1000, LOOPS_PATH=BEDPE, OUT_PATH=str(out), SAVE_PLOTS=False,
+                            MODELLING_LEVEL="gene", GENE_NAME="AAA")
+    with pytest.raises(ValueError, match="GENE_TSV"):
+        model.MultiMM(args)
+    assert not out.exists()
