@@ -4,25 +4,38 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload gw|chrom|region|stress] [--decompose]
 
-Metric (BASELINE.json: "genome-wide minimization wall-time; force evals/s; ..."): combined
-energy+force evaluations per second of the genome-wide system (N = 2e5 beads, flags of
-examples/config_gw.ini).  A step is ONE fused evaluation of every term (prepare -> exact
-all-pairs kernel -> bonded/external pass -> energy reduction) — the thing OpenMM does once per
-L-BFGS line-search trial.  The workload is built the way a user builds it: synthetic .bedpe/.bed
-files in the reference's formats -> loaders -> MultiMM.add_* -> engine (C-ABI).
+Metric (BASELINE.json: "genome-wide minimization wall-time; force evals/s; ensemble
+structures/hour"): the headline `value` is metric 2, combined energy+force evaluations per second
+of the genome-wide system (N = 2e5 beads, flags of examples/config_gw.ini).  A step is ONE fused
+evaluation of every term (prepare -> exact all-pairs kernel -> bonded/external pass -> energy
+reduction) — the thing OpenMM does once per L-BFGS line-search trial.  The workload is built the
+way a user builds it: synthetic .bedpe/.bed files in the reference's formats -> loaders ->
+MultiMM.add_* -> engine (C-ABI).  Metrics 1 and 3 ride on the same line:
 
 `value`  : inputs resident in HBM, K evaluations timed with CUDA events on the engine's stream.
 `e2e`    : the same evaluation through the C-ABI with HOST buffers: positions copied host->device
            and forces device->host every step (what LocalEnergyMinimizer does per evaluation).
-`roofline`: the exact pair kernel against the FP32-FMA peak measured in this run by an FFMA
-           micro-benchmark (MEASURED_PEAKS.json carries only HBM and bf16; this kernel is bound by
-           FP32/MUFU issue, not by HBM or tensor cores).  Algorithmic flops: SURVEY.md 8(d).
-`cpu_baseline`: the CPU oracle (FP64 restatement of the OpenMM Reference semantics, OpenMP) on a
-           bounded sample of the same system.  OpenMM itself is not installable in this image.
+`roofline`: the exact pair kernel against the FP32-FMA peak: `frac` against the FFMA micro-benchmark
+           run inside this bench, `frac_nominal` against 148 SM x 128 lanes x 2 x the maximum SM clock
+           (MEASURED_PEAKS.json carries only HBM and bf16; this kernel is bound by the FP32 / MUFU
+           pipes, not by HBM or tensor cores).  Algorithmic flops: SURVEY.md 8(d).
+`minimize_full` (N = 1): metric 1 — the genome-wide system minimised to OpenMM's default tolerance
+           with unlimited iterations on the exact potential: wall seconds, iterations, evaluations,
+           final energy; and the opt-in two-stage variant (taken from the ensemble member below).
+`ensemble`: metric 3 — every rank runs ONE ensemble member through the driver's own per-replica
+           pipeline (run.run_replica: loaders, init CIF/PSF, force field, minimisation, minimised
+           CIF, per-chromosome CIFs, tar.gz) on its GPU; structures/hour = ranks x 3600 / slowest.
+`decomposed` (N > 1): the N = 2e6 stress system with its pair work shared by the ranks
+           (mmm_dist.cu): ms per evaluation, pair-kernel share, ms in the exchange step.
+`cpu_baseline`: the CPU oracle (FP64 restatement of the OpenMM Reference semantics, OpenMP, thread
+           count set explicitly and reported as measured) on a bounded sample of the same system.
+--impl reference: OpenMM through the unmodified reference (bench_openmm.py) when it imports; else
+           the oracle port, each step a bounded sample scaled by pair count, plus ONE real full-size
+           evaluation timed once.
 N > 1 (torchrun): one independent replica per GPU (ensemble members, seeds = rank), no data-path
 collective; value = evaluations of all ranks / max-over-ranks device time; scaling "weak".
---decompose (N > 1): ONE system (use --workload stress, N = 2e6) whose pair work is shared by the
-ranks, one NCCL all-reduce of forces + energies per evaluation; scaling "strong".
+--decompose (N > 1): headline = ONE system (use --workload stress) whose pair work is shared by the
+ranks; scaling "strong".
 """
 from __future__ import annotations
 
@@ -62,24 +75,31 @@ WORKLOADS = {
 }
 
 
-def build_model(workload: str, seed: int, device: int, tmp: str, with_engine: bool = True):
-    """Synthetic input files -> SimulationConfig -> MultiMM with its force field on the device."""
+def config_kwargs(workload: str, seed: int, tmp: str) -> dict:
+    """Synthetic input files (the reference's formats) and the SimulationConfig fields of a workload."""
     from multimm_b200 import synthetic
-    from multimm_b200.config import SimulationConfig
-    from multimm_b200.model import MultiMM
 
     w = WORKLOADS[workload]
     bedpe = os.path.join(tmp, f"loops_{seed}.bedpe")
     bed = os.path.join(tmp, f"comps_{seed}.bed")
-    synthetic.write_bedpe(bedpe, n_loops=w["n_loops"], seed=100 + seed, chrom=w["chrom"], region=w["region"])
-    synthetic.write_bed(bed, seed=100 + seed, chrom=w["chrom"])
-    kw = dict(PLATFORM="B200", N_BEADS=w["n_beads"], LOOPS_PATH=bedpe, COMPARTMENT_PATH=bed,
+    if not os.path.exists(bedpe):
+        synthetic.write_bedpe(bedpe, n_loops=w["n_loops"], seed=100 + seed, chrom=w["chrom"], region=w["region"])
+        synthetic.write_bed(bed, seed=100 + seed, chrom=w["chrom"])
+    kw = dict(N_BEADS=w["n_beads"], LOOPS_PATH=bedpe, COMPARTMENT_PATH=bed,
               OUT_PATH=os.path.join(tmp, f"out_{seed}"), SHUFFLING_SEED=seed, SAVE_PLOTS=False, **w["flags"])
     if w["chrom"]:
         kw["CHROM"] = w["chrom"]
     if w["region"]:
         kw["LOC_START"], kw["LOC_END"] = w["region"]
-    args = SimulationConfig(**kw)
+    return kw
+
+
+def build_model(workload: str, seed: int, device: int, tmp: str, with_engine: bool = True):
+    """Synthetic input files -> SimulationConfig -> MultiMM with its force field on the device."""
+    from multimm_b200.config import SimulationConfig
+    from multimm_b200.model import MultiMM
+
+    args = SimulationConfig(PLATFORM="B200", **config_kwargs(workload, seed, tmp))
     m = MultiMM(args, device=device)
     m.set_radiuses()
     if with_engine:
@@ -126,16 +146,22 @@ def oracle_system(m, n_sub: int):
 
 def openmm_probe() -> str:
     """is the real reference backend importable (also from a
-    driver-provided baseline/_ref)?  It is not in this image; the answer is recorded in the JSON line."""
-    ref_dir = os.path.join(ROOT, "baseline", "_ref")
-    if os.path.isdir(ref_dir) and ref_dir not in sys.path:
-        sys.path.append(ref_dir)
-    try:
-        import openmm  # noqa: F401
+    driver-provided baseline/_ref)?  The answer is recorded in the JSON line."""
+    import bench_openmm
 
-        return "importable (not used: the OpenMM arm of BASELINE.md section 3 is not written, it could never be run here)"
-    except Exception as e:  # ModuleNotFoundError in this image
-        return f"not importable ({type(e).__name__}): OpenMM-CPU and OpenMM-CUDA are unmeasured"
+    ok, why = bench_openmm.available()
+    return ("importable: `bench.py --impl reference` times the unmodified reference on it" if ok
+            else f"not importable ({why}): OpenMM-CPU and OpenMM-CUDA are unmeasured")
+
+
+def oracle_threads() -> tuple[int, int]:
+    """(threads asked for, threads the OpenMP runtime really gives).  Asked for = the hardware threads
+    of the affinity mask, passed EXPLICITLY: under torchrun OMP_NUM_THREADS=1 is exported, and an
+    oracle left at its default would run on one core while the line says 32."""
+    from oracle import oracle as O
+
+    want = O.host_threads()
+    return want, O.threads_used(want)
 
 
 def cpu_baseline(m, target_seconds: float = 12.0, reps: int = 1):
@@ -144,27 +170,42 @@ def cpu_baseline(m, target_seconds: float = 12.0, reps: int = 1):
     from oracle import oracle as O
 
     n = m.args.N_BEADS
-    cores = os.cpu_count() or 1
+    want, cores = oracle_threads()
     sysd, x = oracle_system(m, min(n, 6000))
-    O.energy_forces(sysd, x)  # warm
+    O.energy_forces(sysd, x, nthreads=want)  # warm
     t0 = time.perf_counter()
-    O.energy_forces(sysd, x)
+    O.energy_forces(sysd, x, nthreads=want)
     probe = time.perf_counter() - t0
     rate = (sysd.n * (sysd.n - 1) / 2) / max(probe, 1e-9)  # pairs/s
     n_sub = int(min(n, max(6000, np.sqrt(2.0 * rate * target_seconds / max(reps, 1)))))
     sysd, x = oracle_system(m, n_sub)
     t0 = time.perf_counter()
     for _ in range(reps):
-        O.energy_forces(sysd, x)
+        O.energy_forces(sysd, x, nthreads=want)
     dt = (time.perf_counter() - t0) / reps
     pairs_sub = n_sub * (n_sub - 1) / 2
     pairs_full = n * (n - 1) / 2
     evals_per_s = (pairs_sub / dt) / pairs_full
     return dict(value=evals_per_s, unit="force_evals/s", cores=cores, kind="port",
-                sample=f"CPU oracle (FP64 restatement of OpenMM Reference semantics, OpenMP x{cores}) on the first "
-                       f"{n_sub} beads of the same system ({pairs_sub:.3g} pairs in {dt:.2f} s), scaled to "
-                       f"{pairs_full:.3g} pairs; OpenMM itself is not installable here (no wheel, no network)",
-                pairs_per_s=pairs_sub / dt, sample_beads=n_sub, sample_seconds=dt, openmm=openmm_probe())
+                sample=f"CPU oracle (FP64 restatement of OpenMM Reference semantics, OpenMP x{cores} threads measured, "
+                       f"{want} requested explicitly) on the first "
+                       f"{n_sub} beads of the same system ({pairs_sub:.3g} pairs in {dt:.2f} s), EXTRAPOLATED to "
+                       f"{pairs_full:.3g} pairs by pair count; OpenMM itself is not installable here (no wheel, no network)",
+                extrapolated=n_sub < n, pairs_per_s=pairs_sub / dt, sample_beads=n_sub, sample_seconds=dt,
+                omp_num_threads_env=os.environ.get("OMP_NUM_THREADS"), openmm=openmm_probe())
+
+
+def oracle_full_evaluation(m) -> dict:
+    """ONE real evaluation of the whole system by the oracle (no sample, no extrapolation)."""
+    from oracle import oracle as O
+
+    want, cores = oracle_threads()
+    sysd, x = oracle_system(m, m.args.N_BEADS)
+    t0 = time.perf_counter()
+    e, _ = O.energy_forces(sysd, x, nthreads=want)
+    dt = time.perf_counter() - t0
+    return dict(seconds=dt, force_evals_per_s=1.0 / dt, cores=cores, beads=int(m.args.N_BEADS),
+                energy_kj_mol=float(e.sum()), note="timed, not extrapolated: every pair of the full system")
 
 
 class ClockSampler:
@@ -238,6 +279,15 @@ def pair_flops(m) -> tuple[float, float]:
     return flops, pairs
 
 
+NOMINAL_SM, NOMINAL_LANES = 148, 128
+
+
+def nominal_fp32_tflops(sm_max_mhz: float | None) -> float:
+    """148 SMs x 128 FP32 lanes x 2 flop x the maximum SM clock (1965 MHz on this pool: 74.4)."""
+    mhz = sm_max_mhz if sm_max_mhz and sm_max_mhz > 0 else 1965.0
+    return NOMINAL_SM * NOMINAL_LANES * 2 * mhz * 1e6 / 1e12
+
+
 def max_over_ranks(values, device):
     """Device timings are reduced with MAX over ranks (no-op for one process)."""
     import torch
@@ -259,6 +309,28 @@ def replica_seed(rank: int) -> int:
     return rank
 
 
+def structures_per_hour(world: int, slowest_seconds: float) -> float:
+    """One ensemble member per rank, all at once: members x 3600 / wall of the slowest."""
+    return world * 3600.0 / slowest_seconds
+
+
+def ensemble_member(workload: str, rank: int, device: int, tmp: str, coarse_cutoff: float) -> dict:
+    """One ensemble member through the driver's per-replica pipeline (multimm_b200.run.run_replica ==
+    one turn of the loop at run.py:473-485): parse inputs, Hilbert start, init CIF + PSF, force
+    field, minimisation to OpenMM's default tolerance, minimised CIF, per-chromosome CIFs, tar.gz."""
+    from multimm_b200 import run
+    from multimm_b200.config import SimulationConfig
+
+    kw = config_kwargs(workload, replica_seed(rank), tmp)
+    kw.update(PLATFORM="B200", GENERATE_ENSEMBLE=True, N_ENSEMBLE=1, MIN_COARSE_CUTOFF=coarse_cutoff)
+    params = SimulationConfig(**kw).model_dump()
+    path = os.path.join(tmp, f"ens_{coarse_cutoff}_{rank}")
+    t0 = time.perf_counter()
+    rep = run.run_replica(params, replica_seed(rank), path, device, archive=True)
+    rep["wall_seconds"] = time.perf_counter() - t0
+    return rep
+
+
 def run_ours(opt):
     import torch
     import torch.distributed as dist
@@ -272,29 +344,33 @@ def run_ours(opt):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     K, W = opt.steps, max(opt.warmup, 3)
     w = WORKLOADS[opt.workload]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def share_dist_id(eng):
+        from multimm_b200.engine import Engine
+
+        box = [Engine.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.dist_init(rank, world, box[0])
 
     with tempfile.TemporaryDirectory(prefix="mmm_bench_") as tmp:
         t_build0 = time.perf_counter()
         decomposed = bool(opt.decompose) and world > 1
         # replicas (default): rank r is ensemble member r.  --decompose: every rank builds the SAME
-        # system and the ranks share its pair work (one all-reduce per evaluation, mmm_dist.cu)
+        # system and the ranks share its pair work (one exchange step per evaluation, mmm_dist.cu)
         m = build_model(opt.workload, seed=0 if decomposed else replica_seed(rank), device=local, tmp=tmp)
         eng = m.engine
         if decomposed:
-            from multimm_b200.engine import Engine
-
-            box = [Engine.dist_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            eng.dist_init(rank, world, box[0])
+            share_dist_id(eng)
         build_s = time.perf_counter() - t_build0
         n = m.args.N_BEADS
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
 
         # ---- device-resident: K evaluations, CUDA events on the engine's stream -----------------
         eng.evaluate_timed(W, flush_l2=True)
@@ -304,7 +380,8 @@ def run_ours(opt):
             total_ms, pair_ms = eng.evaluate_timed(K, flush_l2=True)
             barrier()
         launches = eng.launch_count - launches0
-        total_ms, pair_ms_max = max_over_ranks([total_ms, pair_ms], device=f"cuda:{local}")
+        coll_ms = eng.last_collective_ms if decomposed else 0.0
+        total_ms, pair_ms_max, coll_ms = max_over_ranks([total_ms, pair_ms, coll_ms], device=dev)
         value = whole_job_rate(1 if decomposed else world, K, total_ms)
 
         # ---- end to end through the C-ABI with host buffers ------------------------------------
@@ -323,35 +400,94 @@ def run_ours(opt):
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e_value = whole_job_rate(1 if decomposed else world, K,
-                                   1e3 * max_over_ranks([e2e_s], device=f"cuda:{local}")[0])
+                                   1e3 * max_over_ranks([e2e_s], device=dev)[0])
+
+        # ---- metric 1 (N = 1): the whole minimisation, exact potential, OpenMM's defaults -----------
+        mini = mini_full = None
+        pair_kernel = eng.pair_kernel_in_use
+        if world == 1 and opt.minimize_iters > 0:
+            eng.set_positions(x_np)
+            mini = dict(max_iter=opt.minimize_iters, **eng.minimize(tol=10.0, max_iter=opt.minimize_iters))
+        if world == 1 and not opt.no_minimize_full and opt.workload != "stress":
+            eng.set_positions(x_np)
+            rep = eng.minimize(tol=10.0, max_iter=0)
+            mini_full = dict(exact=dict(rep, tolerance_kj_mol_nm=10.0, max_iter="unlimited",
+                                        potential="exact all-pairs (reference semantics, model.py:886)"))
+        flops, pairs = pair_flops(m)
+        m.close()
+
+        # ---- metric 3: one ensemble member per rank through the driver's pipeline ----------------
+        ens = None
+        if not opt.no_ensemble and opt.workload != "stress" and not decomposed:
+            barrier()
+            member = ensemble_member(opt.workload, rank, local, tmp, opt.coarse_cutoff)
+            slow = max_over_ranks([member["wall_seconds"]], device=dev)[0]
+            keep = ("wall_seconds", "seconds", "iterations", "evaluations", "e_final", "converged", "initialize_s",
+                    "forcefield_s", "minimize_s", "write_cif_s", "coarse_iterations", "coarse_seconds")
+            ens = dict(structures_per_hour=structures_per_hour(world, slow), members=world, gpus=world,
+                       slowest_member_seconds=slow, unit="structures/hour",
+                       mode=(f"opt-in two-stage minimisation (MIN_COARSE_CUTOFF = {opt.coarse_cutoff} nm, then the exact "
+                             "potential to the same stopping rule)" if opt.coarse_cutoff > 0 else
+                             "reference semantics (exact potential throughout)"),
+                       pipeline="run.run_replica: loaders, Hilbert start, init CIF + PSF, force field, minimisation, "
+                                "minimised CIF, per-chromosome CIFs, tar.gz (run.py:473-485)",
+                       rank0_member={k: member[k] for k in keep if k in member})
+            if mini_full is not None and opt.coarse_cutoff > 0:
+                mini_full["two_stage"] = dict(ens["rank0_member"], coarse_cutoff_nm=opt.coarse_cutoff,
+                                              note="minimize_s = both stages; same stopping rule met on the exact potential")
+
+        # ---- N > 1: the N = 2e6 stress system, pair work shared by the ranks ----------------------
+        deco = None
+        if world > 1 and not decomposed and not opt.no_decomposed:
+            barrier()
+            t0 = time.perf_counter()
+            ms_ = build_model("stress", seed=0, device=local, tmp=tmp)
+            share_dist_id(ms_.engine)
+            ms_.engine.evaluate_timed(3, flush_l2=True)
+            barrier()
+            d_tot, d_pair = ms_.engine.evaluate_timed(opt.decomposed_steps, flush_l2=True)
+            barrier()
+            d_coll = ms_.engine.last_collective_ms
+            d_tot, d_pair, d_coll = max_over_ranks([d_tot, d_pair, d_coll], device=dev)
+            ks = opt.decomposed_steps
+            deco = dict(workload=WORKLOADS["stress"]["name"], n_beads=ms_.args.N_BEADS, gpus=world, steps=ks,
+                        ms_per_evaluation=d_tot / ks, force_evals_per_s=ks / (d_tot * 1e-3), scaling="strong",
+                        pair_kernel_ms=d_pair / ks, pair_kernel_share=d_pair / d_tot,
+                        exchange_ms=d_coll, exchange="one NCCL all-reduce (uint64 sum) of the fixed-point force planes and "
+                        "the per-item energy slots, CUDA events around it on the engine's stream, last evaluation",
+                        build_seconds=time.perf_counter() - t0,
+                        single_gpu_reference="profiles/: 1 GPU runs the same system in ms_per_evaluation x speed-up")
+            ms_.close()
 
         if rank != 0:
-            m.close()
             if world > 1:
                 dist.destroy_process_group()
             return
 
-        # ---- rank 0 only: roofline, CPU baseline, a bounded minimisation ------------------------
-        flops, pairs = pair_flops(m)
+        # ---- rank 0 only: roofline, CPU baseline ------------------------------------------------
         if decomposed:  # this rank's kernel evaluates 1 / world of the pairs
             flops, pairs = flops / world, pairs / world
         peak_tflops, mufu_tops = measure_fp32_peak(local)
+        clocks = clk.summary()
+        nominal = nominal_fp32_tflops(clocks.get("sm_max_mhz"))
         pair_ms_avg = pair_ms / K
         achieved = flops / (pair_ms_avg * 1e-3) / 1e12
         traffic = None
         try:  # DRAM bytes of one launch from the committed ncu --set full capture of this kernel
-            with open(os.path.join(ROOT, "profiles", "r01_pair_n3_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "pair_n3_traffic.json")) as fh:
                 tj = json.load(fh)
-            if eng.pair_kernel_in_use == 2 and opt.workload == "gw" and not decomposed:
+            if pair_kernel == 2 and opt.workload == "gw" and not decomposed:
                 traffic = tj["dram_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
-        kernel_name = {1: "k_pair_exact (gather)", 2: "k_pair_n3 (Newton-3)", 3: "k_pair_cells"}.get(eng.pair_kernel_in_use, "none")
+        kernel_name = {1: "k_pair_exact (gather)", 2: "k_pair_n3 (Newton-3)", 3: "k_pair_cells"}.get(pair_kernel, "none")
         roofline = dict(
             bound="fp32", kernel=kernel_name, achieved=achieved, peak=peak_tflops, unit="TFLOP/s",
-            frac=achieved / peak_tflops if peak_tflops > 0 else None, traffic=traffic,
+            frac=achieved / peak_tflops if peak_tflops > 0 else None,
+            peak_nominal=nominal, frac_nominal=achieved / nominal, traffic=traffic,
             traffic_unit="bytes of DRAM per launch (ncu capture under profiles/); the kernel is FMA-pipe bound",
-            peak_source="FFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP32 entry); "
+            peak_source="`peak`: FFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP32 entry; SASS "
+                        "of its loop under profiles/); `peak_nominal`: 148 SM x 128 lanes x 2 x max SM clock; "
                         f"MUFU peak measured likewise: {mufu_tops:.2f} Tera-op/s",
             algorithmic_flops_per_launch=flops, unordered_pairs_per_launch=pairs,
             pair_kernel_ms=pair_ms_avg, pairs_per_s=pairs / (pair_ms_avg * 1e-3),
@@ -359,11 +495,6 @@ def run_ours(opt):
         base = None
         if world == 1 and not opt.no_cpu:
             base = cpu_baseline(m, target_seconds=opt.cpu_seconds)
-        mini = None
-        if opt.minimize_iters > 0 and world == 1:
-            eng.set_positions(x_np)
-            rep = eng.minimize(tol=10.0, max_iter=opt.minimize_iters)
-            mini = dict(max_iter=opt.minimize_iters, **rep)
         out = dict(
             metric="force_evals_per_s", value=value, unit="force_evals/s", n_gpus=world, steps=K, warmup=W,
             ms_per_step=total_ms / K, higher_is_better=True, scaling="strong" if decomposed else "weak",
@@ -371,51 +502,104 @@ def run_ours(opt):
             data="synthetic",
             config=dict(workload=w["name"], n_beads=n, n_loops=int(len(m.ms)), n_bonds=int(m.n_bonds),
                         n_angles=int(m.n_angles), replicas=1 if decomposed else world,
-                        parallelism=(f"one system, pair work sharded over {world} GPUs, 1 NCCL all-reduce per evaluation"
+                        parallelism=(f"one system, pair work sharded over {world} GPUs, 1 exchange step per evaluation"
                                      if decomposed else f"{world} independent replica(s), no collective"), l2="flushed between steps (256 MiB memset inside "
                         "the timed region)", start="Hilbert lattice (0.1 nm)", build_seconds=build_s),
-            clocks=clk.summary(),
+            clocks=clocks,
             e2e=dict(value=e2e_value, unit="force_evals/s", h2d_bytes_per_step=24 * n,
                      d2h_bytes_per_step=24 * n + 8 * len(e_terms)),
             gpu_launches=int(launches),
-            roofline=roofline, cpu_baseline=base, minimize=mini,
+            roofline=roofline, cpu_baseline=base, minimize=mini, minimize_full=mini_full, ensemble=ens,
+            decomposed=deco, exchange_ms=coll_ms if decomposed else None,
             energy_terms={k: float(v) for k, v in zip(("EV", "COB", "SCB", "CHB", "SC", "LAM", "CF", "BOND", "LOOP",
                                                         "ANGLE"), e_terms)},
         )
         print(json.dumps(out), flush=True)
-        m.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def run_reference_openmm(opt, w, tmp):
+    """The real reference: OpenMM through multimm.model.MultiMM, CPU platform on all host threads
+    (the headline of this arm) and, when the platform exists, CUDA on the same GPU."""
+    import bench_openmm
+
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    kw = config_kwargs(opt.workload, 0, tmp)
+    kw["SIM_RUN_MD"] = False
+    cap = max(10.0, min(opt.openmm_minimize_cap, 600.0))
+    arms = {}
+    for plat in ("CPU", "CUDA"):
+        if plat not in bench_openmm.platforms():
+            arms[plat] = dict(unavailable=f"OpenMM has no {plat} platform on this box")
+            continue
+        steps = opt.steps if plat == "CUDA" else max(1, min(opt.steps, 3))  # a CPU evaluation of 2e10 pairs is long
+        try:
+            arms[plat] = bench_openmm.time_arm(kw, plat, steps, min(opt.warmup, 1) if plat == "CPU" else opt.warmup,
+                                               threads, minimize_cap_s=cap)
+        except Exception as e:
+            arms[plat] = dict(unavailable=f"{type(e).__name__}: {e}")
+    cpu = arms["CPU"]
+    if "force_evals_per_s" not in cpu:
+        return None
+    value = cpu["force_evals_per_s"]
+    return dict(
+        impl="reference", metric="force_evals_per_s", value=value, unit="force_evals/s",
+        n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=opt.steps, warmup=opt.warmup, ms_per_step=1e3 / value,
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64/f32 (OpenMM CPU platform)", data="synthetic",
+        config=dict(workload=w["name"], n_beads=w["n_beads"], note="unmodified reference (multimm.model.MultiMM) on OpenMM"),
+        cpu_baseline=dict(value=value, unit="force_evals/s", cores=threads, kind="reference",
+                          sample="full system, every evaluation timed (setPositions + getState(energy, forces))"),
+        e2e=dict(value=value, unit="force_evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        gpu_launches=0, openmm=arms)
+
+
 def run_reference(opt):
-    """The reference arm: OpenMM cannot be installed here, so the reference's CPU implementation is
-    represented by the oracle port on all host cores; each step is a bounded sample."""
+    """The reference arm.  With OpenMM and the reference package importable: the unmodified
+    reference on OpenMM's CPU (and CUDA) platform.  Otherwise (this image): the reference's CPU
+    implementation is represented by the oracle port on all host threads; each step is a bounded
+    sample scaled by pair count, and ONE real full-size evaluation is timed beside them."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    import bench_openmm
+
     K, W = opt.steps, opt.warmup
     w = WORKLOADS[opt.workload]
     with tempfile.TemporaryDirectory(prefix="mmm_bench_ref_") as tmp:
+        ok, why = bench_openmm.available()
+        if ok:
+            out = run_reference_openmm(opt, w, tmp)
+            if out is not None:
+                print(json.dumps(out), flush=True)
+                return
         m = build_model(opt.workload, seed=0, device=0, tmp=tmp, with_engine=False)
-        budget = max(1.0, min(opt.cpu_seconds, 150.0 / max(K + W, 1)))
+        budget = max(1.0, min(opt.cpu_seconds, 120.0 / max(K + W, 1)))
         for _ in range(W):
             base = cpu_baseline(m, target_seconds=budget)
-        vals = []
+        vals, secs = [], []
         t0 = time.perf_counter()
         for _ in range(K):
             base = cpu_baseline(m, target_seconds=budget)
             vals.append(base["value"])
+            secs.append(base["sample_seconds"])
         wall = time.perf_counter() - t0
         value = float(np.mean(vals))
+        full = None
+        if not opt.no_ref_full and m.args.N_BEADS <= 250_000:
+            full = oracle_full_evaluation(m)
         out = dict(
             impl="reference", metric="force_evals_per_s", value=value, unit="force_evals/s",
             n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=K, warmup=W, ms_per_step=1e3 / value,
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-            config=dict(workload=w["name"], n_beads=m.args.N_BEADS, note="each step times a bounded sample and scales "
-                        "by pair count; ms_per_step is the extrapolated time of one full evaluation"),
+            config=dict(workload=w["name"], n_beads=m.args.N_BEADS,
+                        note="EXTRAPOLATED: each step times a bounded bead sample and scales by pair count; ms_per_step "
+                             "is the extrapolated time of one full evaluation, not a timed step.  `full_evaluation` is "
+                             "one real evaluation of the whole system, timed once."),
+            value_is="extrapolated from bounded samples by pair count" if base["extrapolated"] else "timed on the full system",
+            sample_seconds_per_step=float(np.mean(secs)), full_evaluation=full,
             cpu_baseline=dict(base, value=value),
             e2e=dict(value=value, unit="force_evals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-            gpu_launches=0, wall_seconds=wall)
+            gpu_launches=0, wall_seconds=wall, openmm=f"not used: {why}")
         print(json.dumps(out), flush=True)
 
 
@@ -430,7 +614,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--decompose", action="store_true",
                     help="N > 1: one system whose pair work is shared by the ranks (default: one replica per rank)")
-    ap.add_argument("--minimize-iters", type=int, default=50)
+    ap.add_argument("--minimize-iters", type=int, default=50, help="bounded L-BFGS run reported as `minimize` (0: skip)")
+    ap.add_argument("--no-minimize-full", action="store_true", help="skip the full minimisation (metric 1, N = 1 only)")
+    ap.add_argument("--no-ensemble", action="store_true", help="skip the ensemble member per rank (metric 3)")
+    ap.add_argument("--coarse-cutoff", type=float, default=0.5,
+                    help="MIN_COARSE_CUTOFF of the ensemble member in nm (0: reference semantics, exact throughout)")
+    ap.add_argument("--no-decomposed", action="store_true", help="N > 1: skip the sharded N = 2e6 system")
+    ap.add_argument("--decomposed-steps", type=int, default=5)
+    ap.add_argument("--no-ref-full", action="store_true", help="reference arm: skip the one real full-size evaluation")
+    ap.add_argument("--openmm-minimize-cap", type=float, default=120.0)
     opt = ap.parse_args()
     if opt.impl == "reference":
         run_reference(opt)

@@ -203,8 +203,8 @@ int mmm_mean_pair_distance(mmm_handle h, double *mean_out);
 /* ---- one system on several GPUs of one box (exact mode only) -------------------------------- */
 /* The reference has no multi-GPU path (DeviceIndex is never set, model.py:862-876).  Here the
  * O(N^2) pair work of ONE system is dealt to `world` handles, one per GPU / process, each holding
- * the full (replicated) state; one NCCL all-reduce of the fixed-point force planes and of the
- * per-item energies follows the pair kernel of every evaluation.  All ranks must make the same
+ * the full (replicated) state; ONE NCCL all-reduce (uint64 sum) of the fixed-point force planes and
+ * the per-item energy slots follows the pair kernel of every evaluation.  All ranks must make the same
  * calls in the same order.  Results are bit-identical to a single-GPU run.
  *   rank 0: mmm_dist_unique_id(buf, 128); ship buf to the other ranks by any means;
  *   every rank: mmm_dist_init(h, rank, world, buf, 128). */
@@ -213,6 +213,10 @@ int mmm_dist_init(mmm_handle h, int rank, int world, const void *unique_id, int 
 /* Single-GPU emulation of the sharding (tests): the shares of all `world` ranks are run one
  * after another on this handle's GPU into the same accumulators. */
 int mmm_dist_emulate(mmm_handle h, int world);
+/* Milliseconds the exchange step of the most recent evaluation took on this rank (CUDA events on
+ * the handle's stream around the all-reduce; includes the wait for the slowest rank).  0 without a
+ * communicator. */
+int mmm_dist_last_exchange_ms(mmm_handle h, float *ms_out);
 
 /* ---- introspection (tests, bench) ---------------------------------------------------- */
 /* Number of kernels this handle has launched since creation. */

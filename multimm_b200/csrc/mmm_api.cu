@@ -129,13 +129,14 @@ int mmm_destroy(mmm_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_type, h->d_cstr, h->d_s, h->d_bl_ptr, h->d_bl_partner, h->d_bl_flags, h->d_bl_r0, h->d_bl_k,
                   h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_soa, h->d_tiles, h->d_g,
-                  h->d_fpair, h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
+                  h->d_fpair, h->epair_aliased ? nullptr : h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
                   h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs, h->d_v};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   mmm_dist_destroy(h);
-  if (h->d_epair_local) cudaFree(h->d_epair_local);
+  if (h->ev_c0) cudaEventDestroy(h->ev_c0);
+  if (h->ev_c1) cudaEventDestroy(h->ev_c1);
   if (h->h_done) cudaFreeHost(h->h_done);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->d_flush) cudaFree(h->d_flush);
@@ -414,10 +415,11 @@ static int wanted_pair_mode(const mmm_system* h) {
 static void free_scratch(mmm_system* h) {
   cudaStreamSynchronize(h->stream);
   if (h->d_fpair) { cudaFree(h->d_fpair); h->d_fpair = nullptr; }
-  if (h->d_epair) { cudaFree(h->d_epair); h->d_epair = nullptr; }
+  if (h->d_epair && !h->epair_aliased) cudaFree(h->d_epair);
+  h->d_epair = nullptr;
+  h->epair_aliased = false;
   if (h->d_facc) { cudaFree(h->d_facc); h->d_facc = nullptr; }
   if (h->d_items) { cudaFree(h->d_items); h->d_items = nullptr; }
-  if (h->d_epair_local) { cudaFree(h->d_epair_local); h->d_epair_local = nullptr; }
   h->scratch_sig = -1;
 }
 
@@ -447,8 +449,11 @@ static int ensure_scratch(mmm_system* h) {
     if ((rc = dev_alloc(h, &h->d_items, items.size()))) return rc;
     MMM_CUDA(h, cudaMemcpyAsync(h->d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
-    if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
-    MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
+    // several GPUs: the per-item energy slots live behind the force planes in the same allocation,
+    // so that ONE all-reduce (uint64 sum) covers both (mmm_dist.cu)
+    const size_t tail = h->nccl_comm ? 4 * items.size() : 0;
+    if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad + tail))) return rc;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * (3 * (size_t)h->npad + tail), h->stream));
   }
   if (mode == 1 || chb_gather) {
     // gather kernel: items = i-blocks x j-chunks, enough of them that the dynamic scheduler keeps
@@ -478,12 +483,13 @@ static int ensure_scratch(mmm_system* h) {
     if ((rc = dev_alloc(h, &h->d_fpair, cnt))) return rc;
     MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * cnt, h->stream));
   }
-  if ((rc = dev_alloc(h, &h->d_epair, (size_t)h->n_items * 4))) return rc;
-  MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
   if (h->nccl_comm) {
     if (mode != 2) return mmm_fail(h, MMM_ERR_STATE, "the multi-GPU path needs the Newton-3 kernel: default functional forms, EV on, no cut-off");
-    if ((rc = dev_alloc(h, &h->d_epair_local, (size_t)h->n_items * 4))) return rc;
-    MMM_CUDA(h, cudaMemsetAsync(h->d_epair_local, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
+    h->d_epair = reinterpret_cast<double*>(h->d_facc + 3 * (size_t)h->npad);
+    h->epair_aliased = true;
+  } else {
+    if ((rc = dev_alloc(h, &h->d_epair, (size_t)h->n_items * 4))) return rc;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * (size_t)h->n_items * 4, h->stream));
   }
   h->scratch_sig = sig;
   return MMM_OK;

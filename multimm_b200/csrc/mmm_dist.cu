@@ -4,7 +4,7 @@
 // are dealt to the ranks round-robin (item k of rank r is item r + k * world), every rank
 // accumulates its share into its own fixed-point force planes and its own slots of the per-item
 // energy array, then ONE exchange step per evaluation follows:
-//     ncclAllReduce(force planes, uint64 sum)  +  ncclAllReduce(per-item energies, double sum)
+//     ncclAllReduce(force planes + per-item energy slots as bit patterns, uint64 sum)
 // over NVLink, enqueued on the handle's stream between the pair kernel and the O(N) pass.  Integer
 // sums are exact and every energy slot is written by exactly one rank (x + 0 + ... + 0), so all
 // ranks hold bit-identical forces and energies — the same bits a single GPU produces — and the
@@ -57,13 +57,17 @@ int nccl_fail(mmm_system* h, NcclApi* a, ncclResult_t r, const char* what) {
 }  // namespace
 
 // The exchange step: called by mmm_evaluate after the pair kernel when a communicator exists.
+// ONE all-reduce: the per-item energy slots sit behind the force planes in the same allocation and
+// travel as uint64 bit patterns — every slot has exactly one writer and is zero bits on the other
+// ranks, and x + 0 + ... + 0 of the bit patterns is x exactly.
 int mmm_dist_allreduce(mmm_system* h) {
   NcclApi* a = nccl();
   ncclComm_t comm = (ncclComm_t)h->nccl_comm;
-  ncclResult_t r = a->AllReduce(h->d_facc, h->d_facc, 3 * (size_t)h->npad, ncclUint64, ncclSum, comm, h->stream);
-  if (r != ncclSuccess) return nccl_fail(h, a, r, "all-reduce of the force planes");
-  r = a->AllReduce(h->d_epair_local, h->d_epair, (size_t)h->n_items * 4, ncclDouble, ncclSum, comm, h->stream);
-  if (r != ncclSuccess) return nccl_fail(h, a, r, "all-reduce of the energies");
+  const size_t count = 3 * (size_t)h->npad + 4 * (size_t)h->n3_items;
+  MMM_CUDA(h, cudaEventRecord(h->ev_c0, h->stream));
+  ncclResult_t r = a->AllReduce(h->d_facc, h->d_facc, count, ncclUint64, ncclSum, comm, h->stream);
+  if (r != ncclSuccess) return nccl_fail(h, a, r, "all-reduce of the force planes and energy slots");
+  MMM_CUDA(h, cudaEventRecord(h->ev_c1, h->stream));
   return MMM_OK;
 }
 
@@ -108,8 +112,19 @@ int mmm_dist_init(mmm_handle h, int rank, int world, const void* unique_id, int 
     ncclResult_t r = a->CommInitRank(&comm, world, id, rank);
     if (r != ncclSuccess) return nccl_fail(h, a, r, "ncclCommInitRank");
     h->nccl_comm = comm;
+    if (!h->ev_c0) { cudaEventCreate(&h->ev_c0); cudaEventCreate(&h->ev_c1); }
   }
   h->scratch_sig = -2;  // re-size the scratch (local energy slots)
+  return MMM_OK;
+}
+
+int mmm_dist_last_exchange_ms(mmm_handle h, float* ms_out) {
+  if (!h || !ms_out) return MMM_ERR_ARG;
+  *ms_out = 0.f;
+  if (!h->nccl_comm || !h->ev_c0) return MMM_OK;
+  cudaSetDevice(h->device);
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (cudaEventElapsedTime(ms_out, h->ev_c0, h->ev_c1) != cudaSuccess) { cudaGetLastError(); *ms_out = 0.f; }
   return MMM_OK;
 }
 

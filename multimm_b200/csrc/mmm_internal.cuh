@@ -163,7 +163,8 @@ struct mmm_system {
   int dist_rank = 0, dist_world = 1;
   bool dist_emulate = false;     // run every rank's share on this GPU, one after another (tests)
   void* nccl_comm = nullptr;
-  double* d_epair_local = nullptr;  // this rank's energy slots before the all-reduce (dist only)
+  bool epair_aliased = false;    // dist: d_epair is the tail of the d_facc allocation (one all-reduce covers both)
+  cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;  // around the exchange step of the last evaluation (dist)
   int n3_items = 0;              // number of Newton-3 work items (their energy slots come first in d_epair)
   bool n3_chb_only = false;      // the item list is the cut-off mode's CHB-only list
   std::vector<int32_t> h_chrom;  // host copy of the chromosome ids (static; sizes the CHB-only item list)

@@ -702,7 +702,9 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   A.soa = h->d_soa;
   A.tiles = h->d_tiles;
   A.facc = h->d_facc;
-  A.epair = h->nccl_comm ? h->d_epair_local : h->d_epair;
+  A.epair = h->d_epair;
+  // several GPUs: the slots of the other ranks' items must enter the sum as zero bits
+  if (h->nccl_comm) MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * 4 * (size_t)h->n3_items, h->stream));
   A.items = h->d_items;
   A.counter = h->d_counter;
   A.skip = d_skip;

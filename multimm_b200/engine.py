@@ -218,6 +218,13 @@ class Engine:
         """Tests: run the shares of `world` ranks one after another on this GPU."""
         self._ck(self._lib.mmm_dist_emulate(self._h, int(world)))
 
+    @property
+    def last_collective_ms(self) -> float:
+        """ms of the exchange step of the most recent evaluation on this rank (0 without a communicator)."""
+        ms = C.c_float()
+        self._ck(self._lib.mmm_dist_last_exchange_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     # -- introspection ----------------------------------------------------------------------
     @property
     def launch_count(self) -> int:

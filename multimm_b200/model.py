@@ -288,6 +288,8 @@ class MultiMM:
             self.engine.set_cutoff(coarse)
             self.coarse_report = self.engine.minimize(tol=tol, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
             self.engine.set_cutoff(0.0)
+            self.timings["coarse_iterations"] = int(self.coarse_report["iterations"])
+            self.timings["coarse_seconds"] = float(self.coarse_report["wall_seconds"])
         self.report = self.engine.minimize(tol=tol, max_iter=max_iter)
         self.positions = self.engine.get_positions()
         self.timings["minimize_s"] = time.time() - t0

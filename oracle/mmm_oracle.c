@@ -305,6 +305,23 @@ static double eval_angles(int64_t na, const int32_t *ai, const int32_t *aj, cons
 /* full evaluation                                                                       */
 /* ------------------------------------------------------------------------------------ */
 
+/* Threads a parallel region asking for `nthreads` really gets (what bench.py reports as "cores":
+ * launchers such as torchrun export OMP_NUM_THREADS=1, which silently serialises nthreads <= 0). */
+int orc_threads_used(int nthreads) {
+  int got = 1;
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+  {
+#pragma omp single
+    got = omp_get_num_threads();
+  }
+#else
+  (void)nthreads;
+#endif
+  return got;
+}
+
 int orc_energy_forces(const orc_params *p, const double *x, double *e, double *f, int nthreads) {
   const int64_t n = p->n;
   for (int t = 0; t < ORC_NUM_TERMS; t++) e[t] = 0.0;

@@ -57,6 +57,8 @@ typedef struct {
 
 /* Per-term energies e[ORC_NUM_TERMS] and forces f[n*3] (may be NULL) at x[n*3]. */
 int orc_energy_forces(const orc_params *p, const double *x, double *e, double *f, int nthreads);
+/* Number of threads a parallel region that asks for nthreads (<= 0: the OpenMP default) gets. */
+int orc_threads_used(int nthreads);
 /* Number of unordered pairs within the cutoff (or n(n-1)/2 when cutoff == 0). */
 int64_t orc_count_pairs(const orc_params *p, const double *x);
 /* liblbfgs restatement with OpenMM's LocalEnergyMinimizer settings; x is updated in place. */

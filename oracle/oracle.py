@@ -65,6 +65,8 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.orc_energy_forces.restype = C.c_int
         _lib.orc_energy_forces.argtypes = [C.POINTER(_Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.orc_threads_used.restype = C.c_int
+        _lib.orc_threads_used.argtypes = [C.c_int]
         _lib.orc_count_pairs.restype = C.c_int64
         _lib.orc_count_pairs.argtypes = [C.POINTER(_Params), C.c_void_p]
         _lib.orc_minimize.restype = C.c_int
@@ -168,6 +170,19 @@ def energy_forces(sysd: System, x: np.ndarray, want_forces: bool = True, nthread
     f = np.zeros_like(x) if want_forces else None
     lib().orc_energy_forces(C.byref(p), _ptr(x), _ptr(e), _ptr(f), int(nthreads))
     return e, f
+
+
+def host_threads() -> int:
+    """Hardware threads this process may use (affinity mask, not OMP_NUM_THREADS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def threads_used(nthreads: int = 0) -> int:
+    """How many OpenMP threads a call with this `nthreads` argument really runs on."""
+    return int(lib().orc_threads_used(int(nthreads)))
 
 
 def count_pairs(sysd: System, x: np.ndarray) -> int:

@@ -67,11 +67,11 @@ def test_generic_forms(built_lib):
                   {"LAM": 1, "CF": 1, "LOOP": 1}, {"LAM": 2, "CF": 2, "LOOP": 2}, {"LAM": 3}):
         case = make_case(1500, n_chrom=3, seed=11, forms=forms, chb_de=1.0,
                          terms=("EV", "COB", "SCB", "CHB", "SC", "LAM", "CF", "BOND", "LOOP", "ANGLE"))
-        _check(case, e_tol=3e-5, f_tol=2e-4)
+        _check(case)  # the north star's bars: the generic body is FP64 (mmm_pairmath.cuh)
 
 
 def test_non_integer_ev_power(built_lib):
-    _check(make_case(1500, terms=("EV",), ev_power=4.5, seed=7), e_tol=3e-5, f_tol=2e-4)
+    _check(make_case(1500, terms=("EV",), ev_power=4.5, seed=7))
 
 
 def test_hilbert_bit_exact(built_lib):

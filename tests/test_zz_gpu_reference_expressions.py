@@ -21,10 +21,9 @@ AUDIT = json.load(open(os.path.join(GOLD, "forcefield_golden_expressions.json"))
 ALL_ON = dict(EV_USE_EXCLUDED_VOLUME=True, COB_USE_COMPARTMENT_BLOCKS=True, SCB_USE_SUBCOMPARTMENT_BLOCKS=True,
               CHB_USE_CHROMOSOMAL_BLOCKS=True, SC_USE_SPHERICAL_CONTAINER=True, IBL_USE_B_LAMINA_INTERACTION=True,
               CF_USE_CENTRAL_FORCE=True, POL_USE_HARMONIC_BOND=True, LE_USE_HARMONIC_BOND=True, POL_USE_HARMONIC_ANGLE=True)
-# default forms run on the Newton-3 kernel at the north star's bar; the alternate forms run on the
-# generic gather path (lg2/ex2-based powers, Yukawa, step functions) with the looser bar the generic
-# tests of test_gpu_parity.py use, times a safety factor
-TOL = {"default_forms": 1e-5, "fixed_loop_distances": 1e-5, "alt1": 1e-4, "alt2": 1e-4, "alt3": 1e-4}
+# default forms run on the Newton-3 kernel, the alternate forms on the generic gather path (FP64
+# body): the north star's 1e-5 for every one of them
+TOL = {"default_forms": 1e-5, "fixed_loop_distances": 1e-5, "alt1": 1e-5, "alt2": 1e-5, "alt3": 1e-5}
 
 
 @pytest.mark.parametrize("case", list(AUDIT))
