@@ -131,7 +131,8 @@ int mmm_destroy(mmm_handle h) {
                   h->d_an_ptr, h->d_an_ijk, h->d_an_par, h->d_x, h->d_center, h->d_pos4, h->d_soa, h->d_tiles, h->d_g,
                   h->d_fpair, h->epair_aliased ? nullptr : h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
-                  h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs, h->d_v};
+                  h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs, h->d_v,
+                  h->d_soa_sorted, h->d_tiles_sorted, h->d_stage_boxes, h->d_sort_table, h->d_items_cut, h->d_cut_npairs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   mmm_dist_destroy(h);
@@ -300,6 +301,7 @@ int mmm_set_cutoff(mmm_handle h, double rc_nm) {
   if (!h) return MMM_ERR_ARG;
   REQUIRE(h, rc_nm >= 0.0 && isfinite(rc_nm), "mmm_set_cutoff: cutoff must be >= 0");
   h->cutoff = rc_nm;
+  h->sort_age = 0;
   derive_pair_params(h);
   return MMM_OK;
 }
@@ -326,6 +328,7 @@ int mmm_set_positions(mmm_handle h, const double* xyz) {
   int rc = set_center_from_host(h, xyz);
   if (rc) return rc;
   h->positions_set = true;
+  h->sort_age = 0;  // cut-off mode: new positions from outside, rebuild the Morton order
   return MMM_OK;
 }
 
@@ -354,6 +357,7 @@ int mmm_set_positions_device(mmm_handle h, const double* d_xyz) {
   int rc = refresh_center_from_device(h);
   if (rc) return rc;
   h->positions_set = true;
+  h->sort_age = 0;
   return MMM_OK;
 }
 
@@ -376,6 +380,7 @@ int mmm_hilbert_init(mmm_handle h, int p, double spacing_nm) {
   if (rc) return rc;
   if ((rc = refresh_center_from_device(h))) return rc;
   h->positions_set = true;
+  h->sort_age = 0;
   return MMM_OK;
 }
 
@@ -420,16 +425,23 @@ static void free_scratch(mmm_system* h) {
   h->epair_aliased = false;
   if (h->d_facc) { cudaFree(h->d_facc); h->d_facc = nullptr; }
   if (h->d_items) { cudaFree(h->d_items); h->d_items = nullptr; }
+  if (h->d_items_cut) { cudaFree(h->d_items_cut); h->d_items_cut = nullptr; }
+  if (h->d_cut_npairs) { cudaFree(h->d_cut_npairs); h->d_cut_npairs = nullptr; }
   h->scratch_sig = -1;
 }
 
 // Size the pair-kernel work decomposition and its scratch for the kernel that will run.
 static int ensure_scratch(mmm_system* h) {
   const int mode = wanted_pair_mode(h);
-  const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0);
+  // cut-off mode: the default forms run on the Newton-3 machinery over Morton-sorted tiles
+  // (mmm_cutoff.cu), every other form on the cell-list gather kernel (mmm_cells.cu)
+  const bool cut_n3 = mode == 3 && h->pair_kernel_pref != 1 && mmm_pair_n3_eligible(h);
+  const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0) + (cut_n3 ? 64 : 0);
   if (h->scratch_sig == sig) return MMM_OK;
   free_scratch(h);
   h->pair_mode = mode;
+  h->cut_n3 = cut_n3;
+  h->sort_age = 0;
   int rc;
   // cut-off mode with CHB on: an exact CHB-only pass runs beside the cell-list pass — the Newton-3
   // kernel over same-chromosome tile pairs for the polynomial form, the generic gather kernel else
@@ -471,7 +483,21 @@ static int ensure_scratch(mmm_system* h) {
     h->n_items = niblk * nchunk;
     h->n_planes = (int)nchunk;
   }
-  if (mode == 3) {
+  if (cut_n3) {
+    std::vector<int2> items;
+    mmm_n3_build_items(h, items, false);
+    h->n_items_cut = (int)items.size();
+    if ((rc = dev_alloc(h, &h->d_items_cut, items.size()))) return rc;
+    MMM_CUDA(h, cudaMemcpyAsync(h->d_items_cut, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if ((rc = dev_alloc(h, &h->d_cut_npairs, items.size()))) return rc;
+    if (!h->d_facc) {  // CHB off: the planes were not allocated above
+      if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
+      MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
+    }
+    h->cells_item0 = h->n_items;
+    h->n_items += h->n_items_cut;
+  } else if (mode == 3) {
     h->cells_plane = h->n_planes;
     h->cells_item0 = h->n_items;
     h->n_planes += 1;
@@ -509,7 +535,7 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
       only_chb.cutoff2 = 0.0f;
       if ((rc = mmm_launch_pair_exact(h, d_skip, &only_chb))) return rc;
     }
-    rc = mmm_launch_pair_cutoff(h, d_skip);
+    rc = h->cut_n3 ? mmm_launch_pair_cutoff_n3(h, d_skip) : mmm_launch_pair_cutoff(h, d_skip);
   } else if (h->pair_mode == 2) {
     rc = mmm_launch_pair_n3(h, d_skip);
     // the one exchange step per evaluation (every rank enqueues it, converged or not, so that

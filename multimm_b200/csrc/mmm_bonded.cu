@@ -323,8 +323,8 @@ int mmm_upload_angles(mmm_system* h, const int32_t* ai, const int32_t* aj, const
 int mmm_launch_assemble(mmm_system* h, const int* d_skip) {
   AsmArgs A;
   A.x = h->d_x;
-  A.fpair = (h->pair_mode == 1 || h->pair_mode == 3) ? h->d_fpair : nullptr;
-  A.facc = (h->pair_mode == 2 || (h->pair_mode == 3 && h->n3_items > 0 && h->n3_chb_only)) ? h->d_facc : nullptr;
+  A.fpair = (h->pair_mode == 1 || (h->pair_mode == 3 && !h->cut_n3)) ? h->d_fpair : nullptr;
+  A.facc = (h->pair_mode == 2 || (h->pair_mode == 3 && (h->cut_n3 || (h->n3_items > 0 && h->n3_chb_only)))) ? h->d_facc : nullptr;
   A.nchunk = h->n_planes;
   A.n = h->n;
   A.npad = h->npad;

@@ -358,7 +358,7 @@ int64_t mmm_cells_energy_slots(const mmm_system* h) { return (h->n + kCellWarps 
 
 int mmm_cells_alloc(mmm_system* h) {
   if (h->d_keys) return MMM_OK;
-  const size_t n = (size_t)h->n;
+  const size_t n = (size_t)h->npad;  // npad: the buffers are shared with mmm_cutoff.cu, whose order covers the pads
   MMM_CUDA(h, cudaMalloc((void**)&h->d_keys, n * sizeof(uint32_t)));
   MMM_CUDA(h, cudaMalloc((void**)&h->d_keys_tmp, n * sizeof(uint32_t)));
   MMM_CUDA(h, cudaMalloc((void**)&h->d_order, n * sizeof(int)));
@@ -448,6 +448,20 @@ int mmm_get_cell_grid(mmm_handle h, float* cell_out, int32_t* dim_out, float* or
   if (h->pair_mode != 3 || !h->d_keys)
     return mmm_fail(h, MMM_ERR_STATE, "mmm_get_cell_grid: no cut-off evaluation has run on this handle");
   cudaSetDevice(h->device);
+  if (h->cut_n3) {
+    int rc = mmm_cutoff_read_grid(h, cell_out, dim_out, origin_out);
+    if (rc) return rc;
+    if (pairs_in_cutoff) {
+      std::vector<double> per_item((size_t)h->n_items_cut);
+      MMM_CUDA(h, cudaMemcpyAsync(per_item.data(), h->d_cut_npairs, per_item.size() * sizeof(double),
+                                  cudaMemcpyDeviceToHost, h->stream));
+      MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+      double s = 0.0;
+      for (double v : per_item) s += v;  // halves of diagonal stages (ordered pairs) add up to integers
+      *pairs_in_cutoff = (int64_t)(s + 0.5);
+    }
+    return MMM_OK;
+  }
   CellGrid g;
   std::vector<unsigned long long> cnt((size_t)mmm_cells_energy_slots(h));
   MMM_CUDA(h, cudaMemcpyAsync(&g, h->d_cell_grid, sizeof(g), cudaMemcpyDeviceToHost, h->stream));

@@ -201,6 +201,16 @@ struct mmm_system {
   size_t sort_tmp_bytes = 0;
   void* d_cell_grid = nullptr;   // device CellGrid {origin, cell, dim, bits}
   unsigned long long* d_cell_npairs = nullptr;  // ordered pairs inside the cut-off, per CTA
+  // cut-off mode on the Newton-3 machinery (mmm_cutoff.cu; default functional forms)
+  bool cut_n3 = false;           // the cut-off pass runs the CUT variant of k_pair_n3 (else k_pair_cells)
+  float* d_soa_sorted = nullptr;       // [3][npad] coordinate planes in Morton-sorted order
+  TileInfo* d_tiles_sorted = nullptr;  // [npad / 32] boxes of the sorted tiles
+  TileInfo* d_stage_boxes = nullptr;   // [npad / 256] boxes of the sorted stages
+  int* d_sort_table = nullptr;         // radix-sort digit x block table
+  int2* d_items_cut = nullptr;         // all-pairs item table the CUT kernel culls from
+  int n_items_cut = 0;
+  double* d_cut_npairs = nullptr;      // [n_items_cut] pairs inside the cut-off
+  int sort_age = 0;                    // evaluations since the Morton order was rebuilt (0: rebuild now)
   int cells_plane = 0;           // plane of d_fpair the cell-list pass writes
   int64_t cells_item0 = 0;       // first d_epair item of the cell-list pass
 
@@ -241,6 +251,10 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only = false);
 // mmm_dist.cu
 int mmm_dist_allreduce(mmm_system* h);
 void mmm_dist_destroy(mmm_system* h);
+int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip);  // sorted arrays -> d_facc, d_epair (cut-off mode)
+// mmm_cutoff.cu
+int mmm_launch_pair_cutoff_n3(mmm_system* h, const int* d_skip);
+int mmm_cutoff_read_grid(mmm_system* h, float* cell, int32_t* dim, float* origin);
 // mmm_cells.cu
 int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip);
 int64_t mmm_cells_energy_slots(const mmm_system* h);

@@ -104,6 +104,7 @@ struct N3Consts {
   float a_scb[5];  // eps(s) / (rc^2 U), indexed by s + 2
   float a_cob[4];  // by class bits: [1] = A, [2] = B, others 0
   int gk;          // bit 0: SCB on, bit 1: COB on
+  float cut2;      // cut-off^2 (CUT variants): pairs with r^2 >= cut2 contribute nothing
 };
 
 struct N3Args {
@@ -120,6 +121,10 @@ struct N3Args {
   int item_first, item_stride;  // this launch handles items item_first + k * item_stride
   double fscale;             // U * 2^24
   double e_ev, e_gauss, e_chb;  // energy prefactors: eps sigma^p; -rc^2 U; dE
+  // CUT variants (mmm_cutoff.cu): the arrays above are in Morton-sorted order
+  const TileInfo* stage_boxes;  // [npad / 256] bounding box of every j-stage
+  const int* perm;              // sorted slot -> bead id (force emission)
+  double* npairs;               // [n_items] pairs inside the cut-off, per item
   N3Consts c;
 };
 
@@ -179,6 +184,8 @@ __device__ __forceinline__ u64 powi2(u64 w) {
 struct EAcc {
   float ev, scb, cob, chb;
   u64 ev2, chb2;  // packed partial sums of the f32x2 path
+  float cnt;      // CUT: pairs inside the cut-off (reported through the CHB slot, which a CUT pass never uses)
+  u64 cnt2;
 };
 
 // j-beads of a stage, laid out for the packed path: xy[j] = {-x, -x, -y, -y}, z[j] = {-z, -z}
@@ -189,7 +196,7 @@ struct JDup {
 
 // Packed variant of pairs16 for the hot cases (no Gaussians, no self pairs; CHBM 0 or 1): the 8
 // i-beads are processed as 4 register pairs.
-template <int EVP, int CHBM>
+template <int EVP, int CHBM, bool CUT>
 __device__ __forceinline__ void pairs16_packed(const JDup sjd, const int a, const int b, const int jj0,
                                                IBeads& I, float (&cx)[2], float (&cy)[2], float (&cz)[2],
                                                EAcc& E, const N3Consts& c) {
@@ -217,7 +224,12 @@ __device__ __forceinline__ void pairs16_packed(const JDup sjd, const int a, cons
         unpk2(q, qa, qb);
         const u64 wr = pk2(fast_rcp(qa), fast_rcp(qb));  // w / r
         const u64 w = mul2(r, wr);
-        const u64 wp = powi2<EVP>(w);
+        u64 wp = powi2<EVP>(w);
+        if (CUT) {  // plain truncation: the oracle's pair_in_cut on the same FP32 r^2
+          const u64 in2 = pk2(r2a < c.cut2 ? 1.0f : 0.0f, r2b < c.cut2 ? 1.0f : 0.0f);
+          wp = mul2(wp, in2);
+          E.cnt2 = add2(E.cnt2, in2);
+        }
         E.ev2 = add2(E.ev2, wp);
         fs = mul2(wp, wr);
       }
@@ -249,7 +261,7 @@ __device__ __forceinline__ void pairs16_packed(const JDup sjd, const int a, cons
 // GAUSS: evaluate the Gaussian block terms (runtime c.gk says which); CHBM: 0 none, 1 every pair
 // is same-chromosome, 2 compare per pair; SELF: mask i == j (diagonal stages).
 // si4: this lane's i-beads in shared memory (type bits for the slow variants).
-template <int EVP, int GK, int CHBM, bool SELF>
+template <int EVP, int GK, int CHBM, bool SELF, bool CUT>
 __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int a, const int b, const int jj0,
                                         IBeads& I, float (&cx)[2], float (&cy)[2], float (&cz)[2],
                                         EAcc& E, const N3Consts& c, const int* __restrict__ si4,
@@ -272,9 +284,15 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
       const float dx = I.x(ii) - pj.x, dy = I.y(ii) - pj.y, dz = I.z(ii) - pj.z;
       float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
       bool self = false;
+      bool in = true;
+      if (CUT) in = r2 < c.cut2;  // the oracle's pair_in_cut on the same FP32 r^2
       if (SELF) {
         self = (jl - ii) == self_d;
         r2 = self ? 1.0f : r2;
+      }
+      if (CUT) {
+        if (SELF) in = in && !self;
+        E.cnt += in ? 1.0f : 0.0f;
       }
       const float r = fast_sqrt(r2);
       float fs = 0.0f;
@@ -284,6 +302,7 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
         const float w = r * wr;
         float wp = powi<EVP>(w);
         if (SELF) wp = self ? 0.0f : wp;
+        if (CUT) wp = in ? wp : 0.0f;
         E.ev += wp;
         fs = wp * wr;  // -(dE_ev/dr) / r in units of U
       }
@@ -293,6 +312,7 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
         if (GAUSS) {
           float g = fast_ex2(r2 * c.g_c);
           if (SELF) g = self ? 0.0f : g;
+          if (CUT) g = in ? g : 0.0f;
           if (GK & 1) {
             const float t = ((xr & 0x7) == 0) ? aj_scb * g : 0.0f;
             E.scb += t;
@@ -342,7 +362,7 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
 // partners exchange matching beads without selects.  12 + 6 + 3 SHFL.BFLY/FADD pairs leave lane l
 // with the warp's total for j-bead l of the tile (returned in out[3]).  WANT_J false (diagonal
 // stages, ordered pairs): the j side is dropped.
-template <int EVP, int GK, int CHBM, bool SELF, bool WANT_J>
+template <int EVP, int GK, int CHBM, bool SELF, bool WANT_J, bool CUT>
 __device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup sjd, const int a,
                                        const int b, IBeads& I, float (&out)[3], EAcc& E, const N3Consts& c,
                                        const int* __restrict__ si4, const int self_d) {
@@ -352,8 +372,8 @@ __device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup
 #pragma unroll kGroupUnroll
   for (int g = 0; g < 4; ++g) {
     float cx[2], cy[2], cz[2];
-    if constexpr (kPacked) pairs16_packed<EVP, CHBM>(sjd, a, b, 2 * g, I, cx, cy, cz, E, c);
-    else pairs16<EVP, GK, CHBM, SELF>(sj, a, b, 2 * g, I, cx, cy, cz, E, c, si4, self_d);
+    if constexpr (kPacked) pairs16_packed<EVP, CHBM, CUT>(sjd, a, b, 2 * g, I, cx, cy, cz, E, c);
+    else pairs16<EVP, GK, CHBM, SELF, CUT>(sj, a, b, 2 * g, I, cx, cy, cz, E, c, si4, self_d);
     if (!WANT_J) continue;
     if ((g & 1) == 0) {
       s0x = cx[0]; s0y = cy[0]; s0z = cz[0];
@@ -396,7 +416,18 @@ __device__ __forceinline__ void red_fixed(unsigned long long* p, float v, double
   atomicAdd(p, (unsigned long long)q);
 }
 
-template <int EVP, int GK, bool CHB>
+__device__ __forceinline__ float box_dist2(const TileInfo& p, const TileInfo& q) {
+  const float ddx = fmaxf(0.0f, fmaxf(p.lox - q.hix, q.lox - p.hix));
+  const float ddy = fmaxf(0.0f, fmaxf(p.loy - q.hiy, q.loy - p.hiy));
+  const float ddz = fmaxf(0.0f, fmaxf(p.loz - q.hiz, q.loz - p.hiz));
+  return fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+}
+
+// CUT (cut-off mode, mmm_cutoff.cu): the bead arrays are Morton sorted; stages whose box lies beyond
+// the cut-off from the i-block are dropped by one ballot per item, tiles by the classification, pairs
+// by the r^2 < rc^2 mask; forces are emitted through the sort permutation; the number of pairs inside
+// the cut-off is reported in the item's CHB energy slot (a CUT pass never evaluates CHB).
+template <int EVP, int GK, bool CHB, bool CUT>
 __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
   __shared__ __align__(16) float4 s_j[2][N3_JB];
   __shared__ __align__(16) float4 s_jxy[2][N3_JB];
@@ -404,8 +435,13 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
   __shared__ __align__(16) TileInfo s_jt[2][N3_STEPS];
   __shared__ int s_it[N3_IB];  // type bits of the i-block (slow variants)
   __shared__ float s_acc[N3_WARPS][3][N3_JB];
-  __shared__ double s_red[4][N3_WARPS];
+  __shared__ __align__(16) double s_red[4][N3_WARPS];
+  // CUT: per-warp i boxes for the stage cull live in s_red's bytes (used at the start of an item,
+  // s_red at its end, barriers in between) — the static 48 KB are otherwise full
+  TileInfo* const s_ibox = reinterpret_cast<TileInfo*>(&s_red[0][0]);
+  static_assert(sizeof(TileInfo) * N3_WARPS <= sizeof(double) * 4 * N3_WARPS, "s_ibox must fit in s_red");
   __shared__ int s_item;
+  __shared__ unsigned s_mask;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int a = lane >> 2, b = lane & 3;
@@ -424,7 +460,7 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
     const int item = A.item_first + s_item * A.item_stride;
     if (item >= A.n_items) break;
     const int2 it = A.items[item];
-    const int iblk = it.x, js0 = it.y & 0xFFFFFF, js1 = js0 + (it.y >> 24);
+    const int iblk = it.x, js0 = it.y & 0xFFFFFF, cnt = it.y >> 24;
     const int64_t ibase = (int64_t)iblk * N3_IB;
     const int iw = warp * 64 + a * 8;  // first of this lane's i-beads within the block
 
@@ -458,125 +494,157 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
     }
     const bool i_all_pad = ib.cmin >= MMM_PAD_CHROM;
 
-    // first stage
-    {
-      const float4 p0 = A.pos4[(int64_t)js0 * N3_JB + tid];
-      s_j[0][tid] = p0;
-      s_jxy[0][tid] = make_float4(-p0.x, -p0.x, -p0.y, -p0.y);
-      s_jz[0][tid] = make_float2(-p0.z, -p0.z);
+    // which stages of the item are visited: all of them, or (CUT) those whose box is within the
+    // cut-off of some warp's i-beads — thread t of warp 0 tests stage js0 + t, one ballot
+    unsigned todo = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    if (CUT) {
+      if (lane == 0) s_ibox[warp] = ib;
+      __syncthreads();
+      if (warp == 0) {
+        bool keep = false;
+        if (lane < cnt) {
+          const TileInfo sb = A.stage_boxes[js0 + lane];
+          if (sb.cmin < MMM_PAD_CHROM) {
+#pragma unroll
+            for (int w = 0; w < N3_WARPS; ++w) {
+              const TileInfo wb = s_ibox[w];
+              keep = keep || (wb.cmin < MMM_PAD_CHROM && box_dist2(wb, sb) < c.cut2);
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_mask = m;
+      }
+      __syncthreads();
+      todo = s_mask;
     }
-    if (tid < 2 * N3_STEPS)
-      reinterpret_cast<float4*>(s_jt[0])[tid] = reinterpret_cast<const float4*>(A.tiles + (int64_t)js0 * N3_STEPS)[tid];
-    __syncthreads();
 
     double de0 = 0.0, de1 = 0.0, de2 = 0.0, de3 = 0.0, poison = 0.0;
 
-    for (int js = js0; js < js1; ++js) {
-      const int buf = (js - js0) & 1;
-      const bool more = js + 1 < js1;
-      float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f), nxt_t = nxt;
-      if (more) {
-        nxt = A.pos4[(int64_t)(js + 1) * N3_JB + tid];
-        if (tid < 2 * N3_STEPS)
-          nxt_t = reinterpret_cast<const float4*>(A.tiles + (int64_t)(js + 1) * N3_STEPS)[tid];
-      }
-      const bool diag = (js >> 1) == iblk;
-      // global j index minus global i index of (jl = 0, ii = 0): self pair when jl - ii == -that
-      const int self_base = (int)(ibase + iw - (int64_t)js * N3_JB);
-      EAcc E;
-      E.ev = E.scb = E.cob = E.chb = 0.0f;
-      E.ev2 = E.chb2 = pk2(0.0f, 0.0f);
-
-      if (!i_all_pad) {
-        // Classify the stage's 8 tiles at once: lane s < 8 classifies tile s against this warp's
-        // i-beads, the steps fetch their class with one shuffle.  Class: -1 nothing to do;
-        // bits 0-1 CHB mode (0 none, 1 every pair same-chromosome, 2 compare per pair); bit 2
-        // within the Gaussian range.
-        int my_class = -1;
-        if (lane < N3_STEPS) {
-          const TileInfo jt = s_jt[buf][lane];
-          if (jt.cmin < MMM_PAD_CHROM) {  // not padding only
-            int chb_mode = 0;
-            if (CHB) {
-              const bool overlap = !(ib.cmax < jt.cmin || jt.cmax < ib.cmin);
-              const bool uniform = (ib.cmin == ib.cmax) && (jt.cmin == jt.cmax);
-              chb_mode = overlap ? (uniform ? 1 : 2) : 0;
-            }
-            bool near = false;
-            if (GK != 0) {
-              const float ddx = fmaxf(0.0f, fmaxf(ib.lox - jt.hix, jt.lox - ib.hix));
-              const float ddy = fmaxf(0.0f, fmaxf(ib.loy - jt.hiy, jt.loy - ib.hiy));
-              const float ddz = fmaxf(0.0f, fmaxf(ib.loz - jt.hiz, jt.loz - ib.hiz));
-              near = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx)) < c.rg2;
-            }
-            my_class = chb_mode | (near ? 4 : 0);
-            if (EVP == 0 && chb_mode == 0) my_class = -1;  // CHB-only pass: nothing to do for this tile pair
-          }
-        }
-        for (int step = 0; step < N3_STEPS; ++step) {
-          const int cls = __shfl_sync(0xffffffffu, my_class, step);
-          if (cls < 0) continue;
-          const float4* sj = s_j[buf] + step * MMM_TILE;
-          const JDup sjd = {s_jxy[buf] + step * MMM_TILE, s_jz[buf] + step * MMM_TILE};
-          float fj[3];
-          if (diag) {
-            const int self_d = self_base - step * MMM_TILE;
-            step64<EVP, GK, CHB ? 2 : 0, true, false>(sj, sjd, a, b, I, fj, E, c, s_it + iw, self_d);
-            continue;  // ordered pairs: the j side is somebody's i side in this same stage pair
-          }
-          const int chb_mode = cls & 3;
-          if (cls & 4) {
-            if (!CHB || chb_mode == 0) step64<EVP, GK, 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-            else if (chb_mode == 1) step64<EVP, GK, CHB ? 1 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-            else step64<EVP, GK, CHB ? 2 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-          } else if (!CHB || chb_mode == 0) {
-            step64<EVP, 0, 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-          } else if (chb_mode == 1) {
-            step64<EVP, 0, CHB ? 1 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-          } else {
-            step64<EVP, 0, CHB ? 2 : 0, false, true>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-          }
-          // lane (a, b) now holds j-bead 4 a + b = lane of this step; force on j is -sum
-          const int col = step * MMM_TILE + lane;
-          s_acc[warp][0][col] -= fj[0];
-          s_acc[warp][1][col] -= fj[1];
-          s_acc[warp][2][col] -= fj[2];
-        }
-      }
+    if (todo != 0u) {
+      int js = js0 + __ffs(todo) - 1;
+      todo &= todo - 1u;
+      // first stage
       {
-        float lo, hi;
-        unpk2(E.ev2, lo, hi); E.ev += lo + hi;
-        unpk2(E.chb2, lo, hi); E.chb += lo + hi;
+        const float4 p0 = A.pos4[(int64_t)js * N3_JB + tid];
+        s_j[0][tid] = p0;
+        s_jxy[0][tid] = make_float4(-p0.x, -p0.x, -p0.y, -p0.y);
+        s_jz[0][tid] = make_float2(-p0.z, -p0.z);
       }
-      const double wgt = diag ? 0.5 : 1.0;
-      de0 += wgt * (double)E.ev;
-      de1 += wgt * (double)E.cob;
-      de2 += wgt * (double)E.scb;
-      de3 += wgt * (double)E.chb;
+      if (tid < 2 * N3_STEPS)
+        reinterpret_cast<float4*>(s_jt[0])[tid] = reinterpret_cast<const float4*>(A.tiles + (int64_t)js * N3_STEPS)[tid];
+      __syncthreads();
 
-      if (more) {
-        s_j[buf ^ 1][tid] = nxt;
-        s_jxy[buf ^ 1][tid] = make_float4(-nxt.x, -nxt.x, -nxt.y, -nxt.y);
-        s_jz[buf ^ 1][tid] = make_float2(-nxt.z, -nxt.z);
-        if (tid < 2 * N3_STEPS) reinterpret_cast<float4*>(s_jt[buf ^ 1])[tid] = nxt_t;
-      }
-      __syncthreads();
-      if (!diag) {
-        // j-side emission: thread t owns j-bead t of the stage
-        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+      for (int buf = 0;; buf ^= 1) {
+        const bool more = todo != 0u;
+        const int js_next = more ? js0 + __ffs(todo) - 1 : 0;
+        todo &= todo - 1u;
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f), nxt_t = nxt;
+        if (more) {
+          nxt = A.pos4[(int64_t)js_next * N3_JB + tid];
+          if (tid < 2 * N3_STEPS)
+            nxt_t = reinterpret_cast<const float4*>(A.tiles + (int64_t)js_next * N3_STEPS)[tid];
+        }
+        const bool diag = (js >> 1) == iblk;
+        // global j index minus global i index of (jl = 0, ii = 0): self pair when jl - ii == -that
+        const int self_base = (int)(ibase + iw - (int64_t)js * N3_JB);
+        EAcc E;
+        E.ev = E.scb = E.cob = E.chb = E.cnt = 0.0f;
+        E.ev2 = E.chb2 = E.cnt2 = pk2(0.0f, 0.0f);
+
+        if (!i_all_pad) {
+          // Classify the stage's 8 tiles at once: lane s < 8 classifies tile s against this warp's
+          // i-beads, the steps fetch their class with one shuffle.  Class: -1 nothing to do;
+          // bits 0-1 CHB mode (0 none, 1 every pair same-chromosome, 2 compare per pair); bit 2
+          // within the Gaussian range.
+          int my_class = -1;
+          if (lane < N3_STEPS) {
+            const TileInfo jt = s_jt[buf][lane];
+            if (jt.cmin < MMM_PAD_CHROM) {  // not padding only
+              int chb_mode = 0;
+              if (CHB) {
+                const bool overlap = !(ib.cmax < jt.cmin || jt.cmax < ib.cmin);
+                const bool uniform = (ib.cmin == ib.cmax) && (jt.cmin == jt.cmax);
+                chb_mode = overlap ? (uniform ? 1 : 2) : 0;
+              }
+              bool near = false;
+              float d2 = 0.0f;
+              if (GK != 0 || CUT) d2 = box_dist2(ib, jt);
+              if (GK != 0) near = d2 < c.rg2;
+              my_class = chb_mode | (near ? 4 : 0);
+              if (EVP == 0 && chb_mode == 0) my_class = -1;  // CHB-only pass: nothing to do for this tile pair
+              if (CUT && !(d2 < c.cut2)) my_class = -1;      // every pair of the tile pair is beyond the cut-off
+            }
+          }
+          for (int step = 0; step < N3_STEPS; ++step) {
+            const int cls = __shfl_sync(0xffffffffu, my_class, step);
+            if (cls < 0) continue;
+            const float4* sj = s_j[buf] + step * MMM_TILE;
+            const JDup sjd = {s_jxy[buf] + step * MMM_TILE, s_jz[buf] + step * MMM_TILE};
+            float fj[3];
+            if (diag) {
+              const int self_d = self_base - step * MMM_TILE;
+              step64<EVP, GK, CHB ? 2 : 0, true, false, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, self_d);
+              continue;  // ordered pairs: the j side is somebody's i side in this same stage pair
+            }
+            const int chb_mode = cls & 3;
+            if (cls & 4) {
+              if (!CHB || chb_mode == 0) step64<EVP, GK, 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+              else if (chb_mode == 1) step64<EVP, GK, CHB ? 1 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+              else step64<EVP, GK, CHB ? 2 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+            } else if (!CHB || chb_mode == 0) {
+              step64<EVP, 0, 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+            } else if (chb_mode == 1) {
+              step64<EVP, 0, CHB ? 1 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+            } else {
+              step64<EVP, 0, CHB ? 2 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+            }
+            // lane (a, b) now holds j-bead 4 a + b = lane of this step; force on j is -sum
+            const int col = step * MMM_TILE + lane;
+            s_acc[warp][0][col] -= fj[0];
+            s_acc[warp][1][col] -= fj[1];
+            s_acc[warp][2][col] -= fj[2];
+          }
+        }
+        {
+          float lo, hi;
+          unpk2(E.ev2, lo, hi); E.ev += lo + hi;
+          unpk2(E.chb2, lo, hi); E.chb += lo + hi;
+          if (CUT) { unpk2(E.cnt2, lo, hi); E.chb = E.cnt + lo + hi; }
+        }
+        const double wgt = diag ? 0.5 : 1.0;
+        de0 += wgt * (double)E.ev;
+        de1 += wgt * (double)E.cob;
+        de2 += wgt * (double)E.scb;
+        de3 += wgt * (double)E.chb;
+
+        if (more) {
+          s_j[buf ^ 1][tid] = nxt;
+          s_jxy[buf ^ 1][tid] = make_float4(-nxt.x, -nxt.x, -nxt.y, -nxt.y);
+          s_jz[buf ^ 1][tid] = make_float2(-nxt.z, -nxt.z);
+          if (tid < 2 * N3_STEPS) reinterpret_cast<float4*>(s_jt[buf ^ 1])[tid] = nxt_t;
+        }
+        __syncthreads();
+        if (!diag) {
+          // j-side emission: thread t owns j-bead t of the stage
+          float sx = 0.0f, sy = 0.0f, sz = 0.0f;
 #pragma unroll
-        for (int w = 0; w < N3_WARPS; ++w) {
-          sx += s_acc[w][0][tid]; sy += s_acc[w][1][tid]; sz += s_acc[w][2][tid];
-          s_acc[w][0][tid] = 0.0f; s_acc[w][1][tid] = 0.0f; s_acc[w][2][tid] = 0.0f;
+          for (int w = 0; w < N3_WARPS; ++w) {
+            sx += s_acc[w][0][tid]; sy += s_acc[w][1][tid]; sz += s_acc[w][2][tid];
+            s_acc[w][0][tid] = 0.0f; s_acc[w][1][tid] = 0.0f; s_acc[w][2][tid] = 0.0f;
+          }
+          if (sx != 0.0f || sy != 0.0f || sz != 0.0f) {
+            int64_t j = (int64_t)js * N3_JB + tid;
+            if (CUT) j = A.perm[j];
+            red_fixed(A.facc + j, sx, A.fscale, poison);
+            red_fixed(A.facc + A.npad + j, sy, A.fscale, poison);
+            red_fixed(A.facc + 2 * A.npad + j, sz, A.fscale, poison);
+          }
         }
-        const int64_t j = (int64_t)js * N3_JB + tid;
-        if (sx != 0.0f || sy != 0.0f || sz != 0.0f) {
-          red_fixed(A.facc + j, sx, A.fscale, poison);
-          red_fixed(A.facc + A.npad + j, sy, A.fscale, poison);
-          red_fixed(A.facc + 2 * A.npad + j, sz, A.fscale, poison);
-        }
+        __syncthreads();
+        if (!more) break;
+        js = js_next;
       }
-      __syncthreads();
     }
 
     // i-side emission: butterfly over the 4 b-lanes, then lane b emits beads 2b and 2b + 1
@@ -592,7 +660,11 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
       if ((ii >> 1) == b) {
-        const int64_t i = ibase + iw + ii;
+        int64_t i = ibase + iw + ii;
+        if (CUT) {
+          if (I.fx[ii] == 0.0f && I.fy[ii] == 0.0f && I.fz[ii] == 0.0f) continue;  // most i-beads of a culled item
+          i = A.perm[i];
+        }
         red_fixed(A.facc + i, I.fx[ii], A.fscale, poison);
         red_fixed(A.facc + A.npad + i, I.fy[ii], A.fscale, poison);
         red_fixed(A.facc + 2 * A.npad + i, I.fz[ii], A.fscale, poison);
@@ -603,7 +675,7 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
     de0 = de0 * A.e_ev + poison;
     de1 *= A.e_gauss;
     de2 *= A.e_gauss;
-    de3 *= A.e_chb;
+    if (!CUT) de3 *= A.e_chb;  // CUT: the slot carries the number of pairs inside the cut-off
     de0 = warp_sum_d(de0); de1 = warp_sum_d(de1); de2 = warp_sum_d(de2); de3 = warp_sum_d(de3);
     if (lane == 0) { s_red[0][warp] = de0; s_red[1][warp] = de1; s_red[2][warp] = de2; s_red[3][warp] = de3; }
     __syncthreads();
@@ -611,35 +683,80 @@ __global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < N3_WARPS; ++w) s += s_red[tid][w];
+      if (CUT && tid == 3) {
+        A.npairs[item] = s;
+        s = 0.0;
+      }
       A.epair[(size_t)item * 4 + tid] = s;
     }
   }
 }
 
-template <int EVP, int GK, bool CHB>
+template <int EVP, int GK, bool CHB, bool CUT>
 int launch_n3(mmm_system* h, const N3Args& A) {
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pair_n3<EVP, GK, CHB>, N3_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pair_n3<EVP, GK, CHB, CUT>, N3_THREADS, 0);
   if (occ < 1) occ = 1;
   int grid = h->sm_count * occ;
   const int n_local = (A.n_items - A.item_first + A.item_stride - 1) / A.item_stride;
   if (grid > n_local) grid = n_local > 0 ? n_local : 1;
-  k_pair_n3<EVP, GK, CHB><<<grid, N3_THREADS, 0, h->stream>>>(A);
+  k_pair_n3<EVP, GK, CHB, CUT><<<grid, N3_THREADS, 0, h->stream>>>(A);
   return 0;
 }
 
 template <int EVP>
 int launch_n3_evp(mmm_system* h, const N3Args& A, int gk, bool chb) {
   switch (gk * 2 + (chb ? 1 : 0)) {
-    case 0: return launch_n3<EVP, 0, false>(h, A);
-    case 1: return launch_n3<EVP, 0, true>(h, A);
-    case 2: return launch_n3<EVP, 1, false>(h, A);
-    case 3: return launch_n3<EVP, 1, true>(h, A);
-    case 4: return launch_n3<EVP, 2, false>(h, A);
-    case 5: return launch_n3<EVP, 2, true>(h, A);
-    case 6: return launch_n3<EVP, 3, false>(h, A);
-    default: return launch_n3<EVP, 3, true>(h, A);
+    case 0: return launch_n3<EVP, 0, false, false>(h, A);
+    case 1: return launch_n3<EVP, 0, true, false>(h, A);
+    case 2: return launch_n3<EVP, 1, false, false>(h, A);
+    case 3: return launch_n3<EVP, 1, true, false>(h, A);
+    case 4: return launch_n3<EVP, 2, false, false>(h, A);
+    case 5: return launch_n3<EVP, 2, true, false>(h, A);
+    case 6: return launch_n3<EVP, 3, false, false>(h, A);
+    default: return launch_n3<EVP, 3, true, false>(h, A);
   }
+}
+
+template <int EVP>
+int launch_n3_cut(mmm_system* h, const N3Args& A, int gk) {
+  switch (gk) {
+    case 0: return launch_n3<EVP, 0, false, true>(h, A);
+    case 1: return launch_n3<EVP, 1, false, true>(h, A);
+    case 2: return launch_n3<EVP, 2, false, true>(h, A);
+    default: return launch_n3<EVP, 3, false, true>(h, A);
+  }
+}
+
+// constants shared by the exact and the cut-off launch
+void fill_consts(const PairParams& p, bool chb_only, bool with_chb, N3Args& A) {
+  // U = p eps sigma^p in double, from the float parameters the gather kernel uses too (1 in the
+  // CHB-only pass, where EV is not evaluated)
+  const double U = chb_only ? 1.0 : (double)p.ev_power * (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
+  A.fscale = U * N3_FIXED;
+  A.e_ev = chb_only ? 0.0 : (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
+  N3Consts& c = A.c;
+  c.ev_rs = p.ev_rs;
+  c.g_c = p.g_c;
+  c.rg2 = p.rg2;
+  c.chb_kc = p.chb_kc;
+  c.chb_c = (with_chb && p.chb_form >= 0) ? (float)((double)p.chb_de / U) : 0.0f;
+  c.gk = chb_only ? 0 : ((p.scb_form >= 0 ? 1 : 0) | (p.cob_form >= 0 ? 2 : 0));
+  c.cut2 = p.cutoff2;
+  const double rc = p.scb_form >= 0 ? p.scb_rc : p.cob_rc;
+  const double inv = rc > 0.0 ? 1.0 / (rc * rc * U) : 0.0;
+  // s + 2 = 0..4 <-> s = -2..2 ; scb_e = {Ea1 (s=2), Ea2 (s=1), Eb1 (s=-1), Eb2 (s=-2)}
+  c.a_scb[0] = (float)(p.scb_e[3] * inv);
+  c.a_scb[1] = (float)(p.scb_e[2] * inv);
+  c.a_scb[2] = 0.0f;
+  c.a_scb[3] = (float)(p.scb_e[1] * inv);
+  c.a_scb[4] = (float)(p.scb_e[0] * inv);
+  c.a_cob[0] = 0.0f;
+  c.a_cob[1] = (float)(p.cob_ea * inv);
+  c.a_cob[2] = (float)(p.cob_eb * inv);
+  c.a_cob[3] = 0.0f;
+  A.e_gauss = -(rc * rc) * U;
+  A.e_chb = (double)p.chb_de;
 }
 
 }  // namespace
@@ -710,32 +827,11 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   A.skip = d_skip;
   A.npad = h->npad;
   A.n_items = h->n3_items;
-  // U = p eps sigma^p in double, from the float parameters the gather kernel uses too (1 in the
-  // CHB-only pass, where EV is not evaluated)
-  const double U = chb_only ? 1.0 : (double)p.ev_power * (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
-  A.fscale = U * N3_FIXED;
-  A.e_ev = chb_only ? 0.0 : (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
-  N3Consts& c = A.c;
-  c.ev_rs = p.ev_rs;
-  c.g_c = p.g_c;
-  c.rg2 = p.rg2;
-  c.chb_kc = p.chb_kc;
-  c.chb_c = p.chb_form >= 0 ? (float)((double)p.chb_de / U) : 0.0f;
-  c.gk = chb_only ? 0 : ((p.scb_form >= 0 ? 1 : 0) | (p.cob_form >= 0 ? 2 : 0));
-  const double rc = p.scb_form >= 0 ? p.scb_rc : p.cob_rc;
-  const double inv = rc > 0.0 ? 1.0 / (rc * rc * U) : 0.0;
-  // s + 2 = 0..4 <-> s = -2..2 ; scb_e = {Ea1 (s=2), Ea2 (s=1), Eb1 (s=-1), Eb2 (s=-2)}
-  c.a_scb[0] = (float)(p.scb_e[3] * inv);
-  c.a_scb[1] = (float)(p.scb_e[2] * inv);
-  c.a_scb[2] = 0.0f;
-  c.a_scb[3] = (float)(p.scb_e[1] * inv);
-  c.a_scb[4] = (float)(p.scb_e[0] * inv);
-  c.a_cob[0] = 0.0f;
-  c.a_cob[1] = (float)(p.cob_ea * inv);
-  c.a_cob[2] = (float)(p.cob_eb * inv);
-  c.a_cob[3] = 0.0f;
-  A.e_gauss = -(rc * rc) * U;
-  A.e_chb = (double)p.chb_de;
+  A.stage_boxes = nullptr;
+  A.perm = nullptr;
+  A.npairs = nullptr;
+  fill_consts(p, chb_only, true, A);
+  const N3Consts& c = A.c;
 
   const bool timed = !chb_only;  // the CHB-only pass is timed with the cell-list pass
   const bool collect = timed && h->ev_cursor >= 0 && (size_t)(2 * h->ev_cursor + 1) < h->ev_pool.size();
@@ -750,12 +846,41 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
     A.item_first = r;
     A.item_stride = h->dist_world;
     MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
-    if (chb_only) launch_n3<0, 0, true>(h, A);
+    if (chb_only) launch_n3<0, 0, true, false>(h, A);
     else if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
     else launch_n3_evp<3>(h, A, c.gk, chb);
     h->launches++;
   }
   MMM_CUDA(h, cudaGetLastError());
   if (timed) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  return MMM_OK;
+}
+
+// Cut-off mode (mmm_cutoff.cu): EV / COB / SCB truncated at rc over the Morton-sorted arrays; the
+// item table is the all-pairs one, the kernel culls.  Energy slots follow those of the CHB-only pass.
+int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip) {
+  const PairParams& p = h->pp;
+  N3Args A;
+  A.pos4 = h->d_pos4_sorted;
+  A.soa = h->d_soa_sorted;
+  A.tiles = h->d_tiles_sorted;
+  A.facc = h->d_facc;
+  A.epair = h->d_epair + 4 * (size_t)h->cells_item0;
+  A.items = h->d_items_cut;
+  A.counter = h->d_counter + 1;
+  A.skip = d_skip;
+  A.npad = h->npad;
+  A.n_items = h->n_items_cut;
+  A.item_first = 0;
+  A.item_stride = 1;
+  A.stage_boxes = h->d_stage_boxes;
+  A.perm = h->d_order;
+  A.npairs = h->d_cut_npairs;
+  fill_consts(p, false, false, A);
+  MMM_CUDA(h, cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), h->stream));
+  if (p.ev_power == 6.0f) launch_n3_cut<6>(h, A, A.c.gk);
+  else launch_n3_cut<3>(h, A, A.c.gk);
+  h->launches++;
+  MMM_CUDA(h, cudaGetLastError());
   return MMM_OK;
 }

@@ -5,9 +5,12 @@
 //   ffma2+alu    : FFMA2 interleaved 1:1 with independent integer adds — does a packed instruction hold
 //                  the issue port for both of its pipe cycles (then 3 cycles per pair of instructions)
 //                  or only the FMA pipe (then 2)?
-//   ffma2+mufu   : 19 FFMA2 + 8 MUFU per trip (the hot loop's ratio 9.5 : 2 per pair, x2)
+//   ffma2+mufu   : 38 FFMA2 + 8 MUFU per trip (the hot loop's ratio 9.5 : 2 per pair, x4), independent chains:
+//                  do the FMA and the MUFU pipe overlap when nothing depends on anything?
 //   hot          : the hot body itself (EV power 6, far tile, no CHB), register resident, j from shared
-//   hot_rsq      : the same with rsqrt + rcp(r + rs) instead of sqrt + rcp(r^2 + rs r)
+//   hot rsq+rcp  : the same with rsqrt + rcp(r + rs) instead of sqrt + rcp(r^2 + rs r)
+//   hot sqrt+rcp/2 : one MUFU.RCP per TWO pairs (t = 1 / (qa qb); 1/qa = t qb; 1/qb = t qa): 1.5 MUFU per pair
+//   hot rsq+ser4/2 : far tiles only need 1 MUFU per pair: w = y / (1 + rs y), y = rsqrt(r^2), as a series in rs y
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -83,13 +86,15 @@ __global__ void k_ffma2_mufu(float* out, float a, float b) {
   const u64 A = pk2(a, a), B = pk2(b, b);
 #pragma unroll 1
   for (int it = 0; it < ITERS; ++it) {
-    // 19 FFMA2 + 8 MUFU: the hot loop's mix for 4 pairs
+    // 38 FFMA2 + 8 MUFU: the hot loop's mix for 4 pairs (9.5 packed + 2 MUFU each), all independent
 #pragma unroll
     for (int q = 0; q < 8; ++q) { v[q] = fma2(v[q], A, B); asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(m[q])); }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = fma2(v[q], A, B);
+    for (int u = 0; u < 3; ++u)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) v[q] = fma2(v[q], A, B);
+      for (int q = 0; q < 8; ++q) v[q] = fma2(v[q], A, B);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) v[q] = fma2(v[q], A, B);
   }
   float s = 0, lo, hi;
   for (int q = 0; q < 8; ++q) { unpk2(v[q], lo, hi); s += lo + hi + m[q]; }
@@ -145,6 +150,32 @@ __global__ void k_hot(float* out, float rs, int trips) {
             const u64 w3 = mul2(w2, w);
             wp = mul2(w3, w3);
             fs = mul2(wp, wr);
+          } else if (VARIANT == 2) {
+            // one MUFU.RCP for the two halves: t = 1 / (qa qb); 1/qa = t qb, 1/qb = t qa
+            const u64 r = pk2(fsqrt(r2a), fsqrt(r2b));
+            const u64 q = fma2(rs2, r, r2);
+            float qa, qb;
+            unpk2(q, qa, qb);
+            const float t = frcp(qa * qb);
+            const u64 wr = pk2(t * qb, t * qa);
+            const u64 w = mul2(r, wr);
+            const u64 w2 = mul2(w, w);
+            const u64 w3 = mul2(w2, w);
+            wp = mul2(w3, w3);
+            fs = mul2(wp, wr);
+          } else if (VARIANT == 3 || VARIANT == 4) {
+            // far tiles (r >= 0.9 nm, rs / r <= 0.056): w = y / (1 + rs y) as a truncated series in t = rs y
+            const u64 y = pk2(frsq(r2a), frsq(r2b));
+            const u64 t = mul2(rs2, y);
+            const u64 one = pk2(1.0f, 1.0f), mone = pk2(-1.0f, -1.0f);
+            u64 P;
+            if (VARIANT == 3) P = fma2(t, fma2(t, fma2(t, fma2(t, one, mone), one), mone), one);  // 1 - t + t^2 - t^3 + t^4
+            else P = fma2(t, fma2(t, one, mone), one);                                            // 1 - t + t^2
+            const u64 w = mul2(y, P);
+            const u64 w2 = mul2(w, w);
+            const u64 w3 = mul2(w2, w);
+            wp = mul2(w3, w3);
+            fs = mul2(mul2(wp, w), y);
           } else {
             const u64 y = pk2(frsq(r2a), frsq(r2b));
             const u64 r = fma2(r2, y, rs2);  // r + rs
@@ -217,20 +248,24 @@ int main() {
     printf("%-14s %9d %14.3f per (FFMA2 + LOP3) pair: 2 = FFMA2 leaves the issue port free, 3 = it holds it\n",
            "ffma2+alu", wps, cyc(ms, 32.0 * ITERS));
     ms = time_ms([&] { k_ffma2_mufu<<<blocks, threads>>>(out, 1.0000001f, 1e-9f); });
-    printf("%-14s %9d %14.3f per 4 pairs' worth (19 FFMA2 + 8 MUFU): 38 = FMA-pipe bound, 46 = issue-serialised\n",
+    printf("%-14s %9d %14.3f per 4 pairs' worth (38 FFMA2 + 8 MUFU, independent): 76 = FMA-pipe bound, 64 = MUFU bound, 140 = no overlap\n",
            "ffma2+mufu", wps, cyc(ms, 1.0 * ITERS));
   }
   for (int cfg = 0; cfg < 3; ++cfg) {
     const int threads = 256, per_sm = cfg == 0 ? 1 : (cfg == 1 ? 2 : 3), blocks = sms * per_sm, trips = 4096;
-    for (int variant = 0; variant < 2; ++variant) {
+    for (int variant = 0; variant < 5; ++variant) {
       float ms = time_ms([&] {
         if (variant == 0) k_hot<0><<<blocks, threads>>>(out, 0.05f, trips);
-        else k_hot<1><<<blocks, threads>>>(out, 0.05f, trips);
+        else if (variant == 1) k_hot<1><<<blocks, threads>>>(out, 0.05f, trips);
+        else if (variant == 2) k_hot<2><<<blocks, threads>>>(out, 0.05f, trips);
+        else if (variant == 3) k_hot<3><<<blocks, threads>>>(out, 0.05f, trips);
+        else k_hot<4><<<blocks, threads>>>(out, 0.05f, trips);
       });
       const double pairs = 64.0 * trips * (double)blocks * threads;
       const double cyc_pair = ms * 1e-3 * clk / (64.0 * trips * (per_sm * 8 / 4.0));
       printf("%-14s %9d %14.3f cycles per warp-pair per SMSP (floor 19); %.3e pairs/s\n",
-             variant == 0 ? "hot sqrt+rcp" : "hot rsq+rcp", per_sm * 8, cyc_pair, pairs / (ms * 1e-3));
+             variant == 0 ? "hot sqrt+rcp" : variant == 1 ? "hot rsq+rcp" : variant == 2 ? "hot sqrt+rcp/2" :
+             variant == 3 ? "hot rsq+ser4" : "hot rsq+ser2", per_sm * 8, cyc_pair, pairs / (ms * 1e-3));
     }
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));

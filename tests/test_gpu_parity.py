@@ -145,7 +145,7 @@ def test_cutoff_mode_cell_list(built_lib, n, n_chrom, rc, terms):
     assert force_rel_err(f, f_ref) <= F_TOL
     # integer outputs: bit-exact
     grid = eng.cell_grid()
-    assert grid["cell"] >= np.float32(rc) and 1 <= grid["dim"] <= 64
+    assert grid["cell"] == np.float32(rc) and 1 <= grid["dim"] <= 1024  # cells of exactly the cut-off
     order, keys = eng.cell_list()
     xc = (case["x"] - case["x"].mean(axis=0)).astype(np.float32)
     keys_ref, order_ref = O.cell_list(xc, grid["cell"], grid["dim"], grid["origin"])
@@ -158,6 +158,61 @@ def test_cutoff_mode_cell_list(built_lib, n, n_chrom, rc, terms):
     e2, f2 = eng.energy_forces()
     assert np.array_equal(e, e2) and np.array_equal(f, f2)
     eng.close()
+
+
+def test_cutoff_mode_two_kernels_agree(built_lib):
+    """Cut-off mode has two independent implementations: the Newton-3 kernel over Morton-sorted tiles
+    (default forms) and the gather kernel over a cell list (any form; forced with set_pair_kernel(1)).
+    Same truncation, same pair count, energies and forces within the bars of each other and of the oracle."""
+    case = make_case(9000, n_chrom=3, seed=31, terms=("EV", "COB", "SCB", "CHB", "SC", "BOND", "LOOP", "ANGLE"))
+    rc = 0.4
+    eng = to_engine(case, cutoff=rc)
+    e1, f1 = eng.energy_forces()
+    p1 = eng.cell_grid()["pairs"]
+    eng.set_pair_kernel(1)
+    e2, f2 = eng.energy_forces()
+    p2 = eng.cell_grid()["pairs"]
+    eng.close()
+    sysd = to_oracle(case, cutoff=rc)
+    e_ref, f_ref = O.energy_forces(sysd, case["x"])
+    assert p1 == p2 == O.count_pairs(sysd, case["x"])
+    for e in (e1, e2):
+        for t in range(10):
+            assert abs(e[t] - e_ref[t]) <= E_TOL * max(abs(e_ref[t]), 1e-12) + 1e-9, (O.TERM_NAMES[t], e[t], e_ref[t])
+    assert force_rel_err(f1, f_ref) <= F_TOL and force_rel_err(f2, f_ref) <= F_TOL and force_rel_err(f1, f2) <= F_TOL
+
+
+def test_cutoff_mode_outlier_bead(built_lib):
+    """One bead thrown 100 nm out (an L-BFGS trial step can do that): the grid keeps cells of exactly
+    the cut-off (hashed Morton keys, up to 1024 cells per axis), so nothing coarsens; keys, order, pair
+    count and forces still match the oracle, and the evaluation does not degrade towards O(N^2)."""
+    case = make_case(20000, n_chrom=2, seed=41, terms=("EV", "SCB", "BOND", "ANGLE"))
+    case["x"] = case["x"].copy()
+    case["x"][1234] += np.array([100.0, -60.0, 30.0])
+    rc = 0.5
+    eng = to_engine(case, cutoff=rc)
+    e, f = eng.energy_forces()
+    grid = eng.cell_grid()
+    assert grid["cell"] == np.float32(rc) and grid["dim"] > 64
+    sysd = to_oracle(case, cutoff=rc)
+    e_ref, f_ref = O.energy_forces(sysd, case["x"])
+    for t in range(10):
+        assert abs(e[t] - e_ref[t]) <= E_TOL * max(abs(e_ref[t]), 1e-12) + 1e-9, (O.TERM_NAMES[t], e[t], e_ref[t])
+    assert force_rel_err(f, f_ref) <= F_TOL
+    order, keys = eng.cell_list()
+    xc = (case["x"] - case["x"].mean(axis=0)).astype(np.float32)
+    keys_ref, order_ref = O.cell_list(xc, grid["cell"], grid["dim"], grid["origin"])
+    assert np.array_equal(order, order_ref) and np.array_equal(keys, keys_ref)
+    assert grid["pairs"] == O.count_pairs(sysd, case["x"])
+    # cost: the same system without the outlier takes (almost) the same time per evaluation
+    eng.evaluate_timed(3, flush_l2=False)
+    t_out = eng.evaluate_timed(10, flush_l2=False)[0]
+    case["x"][1234] -= np.array([100.0, -60.0, 30.0])
+    eng.set_positions(case["x"])
+    eng.evaluate_timed(3, flush_l2=False)
+    t_in = eng.evaluate_timed(10, flush_l2=False)[0]
+    eng.close()
+    assert t_out <= 1.5 * t_in + 0.5, (t_out, t_in)
 
 
 def test_cutoff_mode_minimizes(built_lib):
