@@ -314,21 +314,30 @@ def structures_per_hour(world: int, slowest_seconds: float) -> float:
     return world * 3600.0 / slowest_seconds
 
 
-def ensemble_member(workload: str, rank: int, device: int, tmp: str, coarse_cutoff: float) -> dict:
-    """One ensemble member through the driver's per-replica pipeline (multimm_b200.run.run_replica ==
-    one turn of the loop at run.py:473-485): parse inputs, Hilbert start, init CIF + PSF, force
-    field, minimisation to OpenMM's default tolerance, minimised CIF, per-chromosome CIFs, tar.gz."""
+def ensemble_members(workload: str, rank: int, world: int, device: int, tmp: str, coarse_cutoff: float, count: int) -> dict:
+    """`count` ensemble members on this rank's GPU through the driver's per-replica pipeline
+    (multimm_b200.run.run_replicas_on_device == the loop at run.py:473-485): parse inputs, Hilbert
+    start, init CIF + PSF, force field, minimisation to OpenMM's default tolerance, minimised CIF,
+    per-chromosome CIFs, tar.gz — the archive of member k is written while member k + 1 minimises.
+    Member seeds: rank, rank + world, ... (replica i -> GPU i mod G, as run.assign_replicas deals them)."""
     from multimm_b200 import run
     from multimm_b200.config import SimulationConfig
 
-    kw = config_kwargs(workload, replica_seed(rank), tmp)
-    kw.update(PLATFORM="B200", GENERATE_ENSEMBLE=True, N_ENSEMBLE=1, MIN_COARSE_CUTOFF=coarse_cutoff)
+    seeds = [replica_seed(rank) + world * k for k in range(count)]
+    kw = config_kwargs(workload, seeds[0], tmp)
+    kw.update(PLATFORM="B200", GENERATE_ENSEMBLE=True, N_ENSEMBLE=max(seeds) + 1, MIN_COARSE_CUTOFF=coarse_cutoff)
     params = SimulationConfig(**kw).model_dump()
-    path = os.path.join(tmp, f"ens_{coarse_cutoff}_{rank}")
+    paths = {i: os.path.join(tmp, f"ens_{coarse_cutoff}_{i}") for i in seeds}
+    got = []
     t0 = time.perf_counter()
-    rep = run.run_replica(params, replica_seed(rank), path, device, archive=True)
-    rep["wall_seconds"] = time.perf_counter() - t0
-    return rep
+    run.run_replicas_on_device(params, paths, seeds, device, True, got.append)
+    wall = time.perf_counter() - t0
+    bad = [p for kind, p in got if kind != "ok"]
+    if bad:
+        raise RuntimeError(f"ensemble member failed: {bad}")
+    reps = [p for kind, p in got if kind == "ok"]
+    run.check_archives(reps)
+    return dict(wall_seconds=wall, members=reps)
 
 
 def run_ours(opt):
@@ -420,20 +429,22 @@ def run_ours(opt):
         ens = None
         if not opt.no_ensemble and opt.workload != "stress" and not decomposed:
             barrier()
-            member = ensemble_member(opt.workload, rank, local, tmp, opt.coarse_cutoff)
-            slow = max_over_ranks([member["wall_seconds"]], device=dev)[0]
-            keep = ("wall_seconds", "seconds", "iterations", "evaluations", "e_final", "converged", "initialize_s",
-                    "forcefield_s", "minimize_s", "write_cif_s", "coarse_iterations", "coarse_seconds")
-            ens = dict(structures_per_hour=structures_per_hour(world, slow), members=world, gpus=world,
-                       slowest_member_seconds=slow, unit="structures/hour",
+            mine = ensemble_members(opt.workload, rank, world, local, tmp, opt.coarse_cutoff, opt.ensemble_members)
+            slow = max_over_ranks([mine["wall_seconds"]], device=dev)[0]
+            keep = ("replica", "seconds", "iterations", "evaluations", "e_final", "converged", "initialize_s",
+                    "forcefield_s", "minimize_s", "write_cif_s", "coarse_iterations", "coarse_seconds", "archive_inline_s")
+            members = world * opt.ensemble_members
+            ens = dict(structures_per_hour=members * 3600.0 / slow, members=members, members_per_gpu=opt.ensemble_members,
+                       gpus=world, slowest_rank_seconds=slow, unit="structures/hour",
                        mode=(f"opt-in two-stage minimisation (MIN_COARSE_CUTOFF = {opt.coarse_cutoff} nm, then the exact "
                              "potential to the same stopping rule)" if opt.coarse_cutoff > 0 else
                              "reference semantics (exact potential throughout)"),
-                       pipeline="run.run_replica: loaders, Hilbert start, init CIF + PSF, force field, minimisation, "
-                                "minimised CIF, per-chromosome CIFs, tar.gz (run.py:473-485)",
-                       rank0_member={k: member[k] for k in keep if k in member})
+                       pipeline="run.run_replicas_on_device: loaders, Hilbert start, init CIF + PSF, force field, minimisation, "
+                                "minimised CIF, per-chromosome CIFs, tar.gz (run.py:473-485); the archive of member k is "
+                                "written on a background thread while member k + 1 minimises",
+                       rank0_members=[{k: r[k] for k in keep if k in r} for r in mine["members"]])
             if mini_full is not None and opt.coarse_cutoff > 0:
-                mini_full["two_stage"] = dict(ens["rank0_member"], coarse_cutoff_nm=opt.coarse_cutoff,
+                mini_full["two_stage"] = dict(ens["rank0_members"][0], coarse_cutoff_nm=opt.coarse_cutoff,
                                               note="minimize_s = both stages; same stopping rule met on the exact potential")
 
         # ---- N > 1: the N = 2e6 stress system, pair work shared by the ranks ----------------------
@@ -617,6 +628,7 @@ def main():
     ap.add_argument("--minimize-iters", type=int, default=50, help="bounded L-BFGS run reported as `minimize` (0: skip)")
     ap.add_argument("--no-minimize-full", action="store_true", help="skip the full minimisation (metric 1, N = 1 only)")
     ap.add_argument("--no-ensemble", action="store_true", help="skip the ensemble member per rank (metric 3)")
+    ap.add_argument("--ensemble-members", type=int, default=2, help="ensemble members per rank (metric 3)")
     ap.add_argument("--coarse-cutoff", type=float, default=0.5,
                     help="MIN_COARSE_CUTOFF of the ensemble member in nm (0: reference semantics, exact throughout)")
     ap.add_argument("--no-decomposed", action="store_true", help="N > 1: skip the sharded N = 2e6 system")

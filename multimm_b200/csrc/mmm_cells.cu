@@ -357,19 +357,25 @@ void launch_cells_evp(const CellArgs& A, int gk, int blocks, cudaStream_t st) {
 int64_t mmm_cells_energy_slots(const mmm_system* h) { return (h->n + kCellWarps * 32 - 1) / (kCellWarps * 32); }
 
 int mmm_cells_alloc(mmm_system* h) {
-  if (h->d_keys) return MMM_OK;
-  const size_t n = (size_t)h->npad;  // npad: the buffers are shared with mmm_cutoff.cu, whose order covers the pads
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_keys, n * sizeof(uint32_t)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_keys_tmp, n * sizeof(uint32_t)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_order, n * sizeof(int)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_order_tmp, n * sizeof(int)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_pos4_sorted, n * sizeof(float4)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_start, (size_t)2 * kMaxCodes * sizeof(int)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_grid, sizeof(CellGrid)));
-  MMM_CUDA(h, cudaMalloc((void**)&h->d_cell_npairs, (size_t)mmm_cells_energy_slots(h) * sizeof(unsigned long long)));
+  // every buffer on its own: some are shared with mmm_cutoff.cu (which may have run first on this handle)
+  const size_t n = (size_t)h->npad;  // npad: the shared order covers the pads
+  auto need = [&](void** p, size_t bytes) -> int {
+    if (*p) return MMM_OK;
+    MMM_CUDA(h, cudaMalloc(p, bytes));
+    return MMM_OK;
+  };
+  int rc;
+  if ((rc = need((void**)&h->d_keys, n * sizeof(uint32_t)))) return rc;
+  if ((rc = need((void**)&h->d_keys_tmp, n * sizeof(uint32_t)))) return rc;
+  if ((rc = need((void**)&h->d_order, n * sizeof(int)))) return rc;
+  if ((rc = need((void**)&h->d_order_tmp, n * sizeof(int)))) return rc;
+  if ((rc = need((void**)&h->d_pos4_sorted, n * sizeof(float4)))) return rc;
+  if ((rc = need((void**)&h->d_cell_start, (size_t)2 * kMaxCodes * sizeof(int)))) return rc;
+  if ((rc = need((void**)&h->d_cell_grid, sizeof(CellGrid)))) return rc;
+  if ((rc = need((void**)&h->d_cell_npairs, (size_t)mmm_cells_energy_slots(h) * sizeof(unsigned long long)))) return rc;
   // per-cell histogram + placement cursor
   h->sort_tmp_bytes = (size_t)2 * kMaxCodes * sizeof(int);
-  MMM_CUDA(h, cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes));
+  if ((rc = need(&h->d_sort_tmp, h->sort_tmp_bytes))) return rc;
   return MMM_OK;
 }
 

@@ -63,6 +63,9 @@ constexpr int kGroupUnroll = N3_GROUP_UNROLL;
 #ifndef N3_USE_F32X2
 #define N3_USE_F32X2 1
 #endif
+#ifndef N3_MIN_BLOCKS
+#define N3_MIN_BLOCKS 2  // resident CTAs per SM the register budget is set for (2: 128 registers; 3: 80)
+#endif
 
 static_assert(N3_IB == MMM_PAD_TO, "npad must be a multiple of the i-block");
 static_assert(N3_IB == N3_WARPS * 64, "a warp owns 64 i-beads");
@@ -428,7 +431,7 @@ __device__ __forceinline__ float box_dist2(const TileInfo& p, const TileInfo& q)
 // by the r^2 < rc^2 mask; forces are emitted through the sort permutation; the number of pairs inside
 // the cut-off is reported in the item's CHB energy slot (a CUT pass never evaluates CHB).
 template <int EVP, int GK, bool CHB, bool CUT>
-__global__ void __launch_bounds__(N3_THREADS, 2) k_pair_n3(const N3Args A) {
+__global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3Args A) {
   __shared__ __align__(16) float4 s_j[2][N3_JB];
   __shared__ __align__(16) float4 s_jxy[2][N3_JB];
   __shared__ __align__(8) float2 s_jz[2][N3_JB];

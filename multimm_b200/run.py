@@ -256,8 +256,42 @@ def assign_replicas(n_ensemble: int, devices: list[int]) -> dict[int, list[int]]
     return plan
 
 
-def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool = True) -> dict:
-    """One ensemble member: SHUFFLING_SEED = i, OUT_PATH = run_<i> (run.py:473-485)."""
+class Archiver:
+    """tar.gz of finished run directories on a background thread, so that replica k is archived while
+    replica k + 1 minimises on the GPU (gzip and the engine's C calls both release the GIL).  The
+    reference archives inline (run.py:478-485); the files written are the same."""
+
+    def __init__(self):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mmm-archive")
+        self.pending = []
+
+    def submit(self, run_path: str):
+        t0 = time.time()
+
+        def job():
+            tar = archive_run(run_path)
+            return tar, time.time() - t0
+
+        self.pending.append(self.pool.submit(job))
+
+    def wait(self) -> float:
+        """Block until every archive is written; returns the seconds spent archiving (summed).
+        Re-raises the first failure (a run directory that was not deleted because its archive failed)."""
+        spent = 0.0
+        try:
+            for fut in self.pending:
+                spent += fut.result()[1]
+        finally:
+            self.pending = []
+            self.pool.shutdown(wait=True)
+        return spent
+
+
+def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool = True, archiver: Archiver | None = None) -> dict:
+    """One ensemble member: SHUFFLING_SEED = i, OUT_PATH = run_<i> (run.py:473-485).  With an
+    `archiver` the tar.gz is written in the background (the report names the file it will be)."""
     from .model import MultiMM
 
     cfg = SimulationConfig(**{**params, "SHUFFLING_SEED": i, "OUT_PATH": run_path})
@@ -270,16 +304,35 @@ def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool 
         md.close()
     out = dict(replica=i, device=device, seconds=time.time() - t0, **(rep or {}), **md.timings)
     if archive:
-        out["archive"] = archive_run(run_path)
+        t1 = time.time()
+        if archiver is not None:
+            archiver.submit(run_path)
+            out["archive"] = run_path + ".tar.gz"
+        else:
+            out["archive"] = archive_run(run_path)
+        out["archive_inline_s"] = time.time() - t1
     return out
 
 
+def run_replicas_on_device(params: dict, paths: list[str], todo: list[int], device: int, archive: bool, emit):
+    """The replicas dealt to one GPU, one after another; archives overlap the next minimisation."""
+    archiver = Archiver() if archive else None
+    try:
+        for i in todo:
+            try:
+                emit(("ok", run_replica(params, i, paths[i], device, archive, archiver)))
+            except Exception as e:  # report and keep going with the next replica
+                emit(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
+    finally:
+        if archiver is not None:
+            try:
+                archiver.wait()
+            except Exception as e:
+                emit(("error", dict(replica=-1, device=device, error=f"archive failed: {type(e).__name__}: {e}")))
+
+
 def _worker(params: dict, paths: list[str], todo: list[int], device: int, archive: bool, queue):
-    for i in todo:
-        try:
-            queue.put(("ok", run_replica(params, i, paths[i], device, archive)))
-        except Exception as e:  # report and keep going with the next replica
-            queue.put(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
+    run_replicas_on_device(params, paths, todo, device, archive, queue.put)
 
 
 def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -> list[dict]:
@@ -293,7 +346,14 @@ def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -
     paths = replica_paths(args.OUT_PATH, n)
     plan = assign_replicas(n, devices)
     if len(devices) == 1:
-        return [run_replica(params, i, paths[i], devices[0], archive) for i in range(n)]
+        got = []
+        run_replicas_on_device(params, paths, list(range(n)), devices[0], archive, got.append)
+        errors = [p for kind, p in got if kind != "ok"]
+        if errors:
+            raise RuntimeError(f"{len(errors)} ensemble member(s) failed: {errors}")
+        results = [p for kind, p in got if kind == "ok"]
+        check_archives(results)
+        return results
     ctx = mp.get_context("spawn")  # CUDA contexts must not be forked
     queue = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(params, paths, todo, dev, archive, queue))
@@ -304,13 +364,22 @@ def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -
         results, errors = collect_reports(procs, queue, n)
     finally:
         for p in procs:
-            p.join(timeout=60)  # workers exit by themselves once their replicas are reported
+            p.join(timeout=900)  # workers exit by themselves once their replicas are reported and archived
             if p.is_alive():
                 p.terminate()  # exact processes we started
                 p.join()
     if errors:
         raise RuntimeError(f"{len(errors)} ensemble member(s) failed: {errors}")
+    check_archives(results)
     return sorted(results, key=lambda r: r["replica"])
+
+
+def check_archives(results: list[dict]):
+    """Archives are written in the background: once the workers are done every tarball must exist and
+    be non-empty (archive_run keeps the run directory otherwise, run.py:436-443)."""
+    bad = [r["archive"] for r in results if "archive" in r and not (os.path.exists(r["archive"]) and os.path.getsize(r["archive"]) > 0)]
+    if bad:
+        raise RuntimeError(f"archive(s) missing after the ensemble finished: {bad}")
 
 
 def collect_reports(procs, queue, n: int, poll_seconds: float = 2.0):

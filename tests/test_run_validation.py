@@ -270,3 +270,28 @@ def test_unavailable_integrator_and_platform_fail_before_any_work():
     args_tests(make_config(SIM_RUN_MD=True, SIM_INTEGRATOR_TYPE="langevin", PLATFORM="OpenCL"))
     with pytest.raises(ValueError, match="PLATFORM"):
         args_tests(make_config(PLATFORM="TPU"))
+
+
+def test_archiver_runs_in_the_background_and_reports_failures(tmp_path):
+    """Replica k is archived while replica k + 1 runs: same tar.gz as run.py:423-445 writes inline;
+    a failed archive surfaces at wait() and leaves the run directory in place."""
+    import tarfile
+
+    from multimm_b200 import run
+
+    ok = tmp_path / "run_0"
+    (ok / "model").mkdir(parents=True)
+    (ok / "model" / "MultiMM_minimized.cif").write_text("data\n" * 1000)
+    arch = run.Archiver()
+    arch.submit(str(ok))
+    assert arch.wait() >= 0.0
+    assert tarfile.is_tarfile(str(ok) + ".tar.gz") and not ok.exists()
+    with tarfile.open(str(ok) + ".tar.gz") as t:
+        assert "run_0/model/MultiMM_minimized.cif" in t.getnames()
+    run.check_archives([dict(archive=str(ok) + ".tar.gz")])
+    with pytest.raises(RuntimeError, match="missing"):
+        run.check_archives([dict(archive=str(tmp_path / "nope.tar.gz"))])
+    arch = run.Archiver()
+    arch.submit(str(tmp_path / "does_not_exist"))
+    with pytest.raises(Exception):
+        arch.wait()
