@@ -451,6 +451,8 @@ static int ensure_scratch(mmm_system* h) {
   h->n3_items = 0;
   h->n_planes = 0;
   h->nchunk = 1;
+  std::vector<int2> items_cut;
+  if (cut_n3) mmm_n3_build_items(h, items_cut, false);
   if (mode == 2 || chb_n3) {
     // Newton-3: fixed-point force planes + work-item table
     std::vector<int2> items;
@@ -461,9 +463,11 @@ static int ensure_scratch(mmm_system* h) {
     if ((rc = dev_alloc(h, &h->d_items, items.size()))) return rc;
     MMM_CUDA(h, cudaMemcpyAsync(h->d_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (mode == 2 || chb_n3 || cut_n3) {
     // several GPUs: the per-item energy slots live behind the force planes in the same allocation,
     // so that ONE all-reduce (uint64 sum) covers both (mmm_dist.cu)
-    const size_t tail = h->nccl_comm ? 4 * items.size() : 0;
+    const size_t tail = h->nccl_comm ? 4 * ((size_t)h->n3_items + items_cut.size()) : 0;
     if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad + tail))) return rc;
     MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * (3 * (size_t)h->npad + tail), h->stream));
   }
@@ -484,17 +488,15 @@ static int ensure_scratch(mmm_system* h) {
     h->n_planes = (int)nchunk;
   }
   if (cut_n3) {
-    std::vector<int2> items;
-    mmm_n3_build_items(h, items, false);
+    const std::vector<int2>& items = items_cut;
     h->n_items_cut = (int)items.size();
+    h->h_cut_iblk.resize(items.size());
+    for (size_t q = 0; q < items.size(); ++q) h->h_cut_iblk[q] = items[q].x;
     if ((rc = dev_alloc(h, &h->d_items_cut, items.size()))) return rc;
     MMM_CUDA(h, cudaMemcpyAsync(h->d_items_cut, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
     if ((rc = dev_alloc(h, &h->d_cut_npairs, items.size()))) return rc;
-    if (!h->d_facc) {  // CHB off: the planes were not allocated above
-      if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad))) return rc;
-      MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * 3 * (size_t)h->npad, h->stream));
-    }
+    MMM_CUDA(h, cudaMemsetAsync(h->d_cut_npairs, 0, sizeof(double) * items.size(), h->stream));
     h->cells_item0 = h->n_items;
     h->n_items += h->n_items_cut;
   } else if (mode == 3) {
@@ -510,7 +512,9 @@ static int ensure_scratch(mmm_system* h) {
     MMM_CUDA(h, cudaMemsetAsync(h->d_fpair, 0, sizeof(double) * cnt, h->stream));
   }
   if (h->nccl_comm) {
-    if (mode != 2) return mmm_fail(h, MMM_ERR_STATE, "the multi-GPU path needs the Newton-3 kernel: default functional forms, EV on, no cut-off");
+    const bool chb_ok = h->pp.chb_form < 0 || h->pp.chb_form == MMM_CHB_POLYNOMIAL;
+    if (!(mode == 2 || (cut_n3 && chb_ok)))
+      return mmm_fail(h, MMM_ERR_STATE, "the multi-GPU path needs the Newton-3 kernel: default functional forms, EV on");
     h->d_epair = reinterpret_cast<double*>(h->d_facc + 3 * (size_t)h->npad);
     h->epair_aliased = true;
   } else {
@@ -526,6 +530,8 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
   if (h->topo_dirty && (rc = mmm_upload_topology(h))) return rc;
   if ((rc = ensure_scratch(h))) return rc;
   if ((rc = mmm_launch_prepare(h, d_skip))) return rc;
+  // several GPUs: the energy slots of the other ranks' items must enter the all-reduce as zero bits
+  if (h->nccl_comm) MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * 4 * (size_t)h->n_items, h->stream));
   if (h->pair_mode == 3) {
     if (h->pp.chb_form == MMM_CHB_POLYNOMIAL) {
       if ((rc = mmm_launch_pair_n3(h, d_skip, true))) return rc;
@@ -536,6 +542,7 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
       if ((rc = mmm_launch_pair_exact(h, d_skip, &only_chb))) return rc;
     }
     rc = h->cut_n3 ? mmm_launch_pair_cutoff_n3(h, d_skip) : mmm_launch_pair_cutoff(h, d_skip);
+    if (!rc && h->nccl_comm) rc = mmm_dist_allreduce(h);
   } else if (h->pair_mode == 2) {
     rc = mmm_launch_pair_n3(h, d_skip);
     // the one exchange step per evaluation (every rank enqueues it, converged or not, so that

@@ -63,7 +63,7 @@ int nccl_fail(mmm_system* h, NcclApi* a, ncclResult_t r, const char* what) {
 int mmm_dist_allreduce(mmm_system* h) {
   NcclApi* a = nccl();
   ncclComm_t comm = (ncclComm_t)h->nccl_comm;
-  const size_t count = 3 * (size_t)h->npad + 4 * (size_t)h->n3_items;
+  const size_t count = 3 * (size_t)h->npad + 4 * (size_t)h->n_items;
   MMM_CUDA(h, cudaEventRecord(h->ev_c0, h->stream));
   ncclResult_t r = a->AllReduce(h->d_facc, h->d_facc, count, ncclUint64, ncclSum, comm, h->stream);
   if (r != ncclSuccess) return nccl_fail(h, a, r, "all-reduce of the force planes and energy slots");
@@ -95,7 +95,6 @@ int mmm_dist_unique_id(void* out, int nbytes) {
 int mmm_dist_init(mmm_handle h, int rank, int world, const void* unique_id, int nbytes) {
   if (!h) return MMM_ERR_ARG;
   if (world < 1 || rank < 0 || rank >= world) return mmm_fail(h, MMM_ERR_ARG, "mmm_dist_init: need 0 <= rank < world");
-  if (h->cutoff > 0.0) return mmm_fail(h, MMM_ERR_STATE, "mmm_dist_init: the sharded path is the exact (NoCutoff) one; set the cut-off to 0");
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   mmm_dist_destroy(h);

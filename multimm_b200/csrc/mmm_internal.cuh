@@ -209,6 +209,7 @@ struct mmm_system {
   int* d_sort_table = nullptr;         // radix-sort digit x block table
   int2* d_items_cut = nullptr;         // all-pairs item table the CUT kernel culls from
   int n_items_cut = 0;
+  std::vector<int32_t> h_cut_iblk;     // i-block of every item of d_items_cut (slab boundaries of the sharded mode)
   double* d_cut_npairs = nullptr;      // [n_items_cut] pairs inside the cut-off
   int sort_age = 0;                    // evaluations since the Morton order was rebuilt (0: rebuild now)
   int cells_plane = 0;           // plane of d_fpair the cell-list pass writes

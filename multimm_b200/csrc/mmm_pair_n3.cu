@@ -823,8 +823,6 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   A.tiles = h->d_tiles;
   A.facc = h->d_facc;
   A.epair = h->d_epair;
-  // several GPUs: the slots of the other ranks' items must enter the sum as zero bits
-  if (h->nccl_comm) MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * 4 * (size_t)h->n3_items, h->stream));
   A.items = h->d_items;
   A.counter = h->d_counter;
   A.skip = d_skip;
@@ -880,10 +878,25 @@ int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip) {
   A.perm = h->d_order;
   A.npairs = h->d_cut_npairs;
   fill_consts(p, false, false, A);
-  MMM_CUDA(h, cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), h->stream));
-  if (p.ev_power == 6.0f) launch_n3_cut<6>(h, A, A.c.gk);
-  else launch_n3_cut<3>(h, A, A.c.gk);
-  h->launches++;
+  // Several GPUs: the sorted order is cut into contiguous slabs of i-blocks — spatial slabs along
+  // the Morton curve — and rank r evaluates the items of its slab (pairs with the stages at or above
+  // its diagonal, i.e. its own beads and the halo towards the higher slabs within the cut-off); the
+  // j-side forces that land on other slabs' beads travel in the all-reduce of the force planes.
+  const int nib = (int)(h->npad / N3_IB);
+  const int r0 = h->dist_emulate ? 0 : h->dist_rank, r1 = h->dist_emulate ? h->dist_world : h->dist_rank + 1;
+  for (int r = r0; r < r1; ++r) {
+    const int b0 = (int)((int64_t)nib * r / h->dist_world), b1 = (int)((int64_t)nib * (r + 1) / h->dist_world);
+    const auto& ib = h->h_cut_iblk;
+    A.item_first = (int)(std::lower_bound(ib.begin(), ib.end(), b0) - ib.begin());
+    A.n_items = (int)(std::lower_bound(ib.begin(), ib.end(), b1) - ib.begin());
+    A.item_stride = 1;
+    if (h->dist_world == 1) { A.item_first = 0; A.n_items = h->n_items_cut; }
+    if (A.n_items <= A.item_first) continue;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), h->stream));
+    if (p.ev_power == 6.0f) launch_n3_cut<6>(h, A, A.c.gk);
+    else launch_n3_cut<3>(h, A, A.c.gk);
+    h->launches++;
+  }
   MMM_CUDA(h, cudaGetLastError());
   return MMM_OK;
 }

@@ -249,6 +249,31 @@ def test_sharded_pair_work_is_bit_identical(built_lib, world):
     assert np.array_equal(x1, x2)
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_cutoff_mode_is_bit_identical(built_lib, world):
+    """Cut-off mode on several GPUs: the Morton-sorted order is cut into contiguous slabs of i-blocks
+    (spatial slabs along the curve), rank r evaluates its slab against itself and the stages above it
+    within the cut-off, CHB's exact pass is dealt round-robin; one all-reduce of the fixed-point planes
+    combines them.  Emulated on one GPU: same bits as the unsharded cut-off run."""
+    case = make_case(7000, n_chrom=3, seed=78)
+    eng = to_engine(case, cutoff=0.45)
+    e1, f1 = eng.energy_forces()
+    p1 = eng.cell_grid()["pairs"]
+    rep1 = eng.minimize(tol=10.0, max_iter=10)
+    x1 = eng.get_positions()
+    eng.close()
+    eng = to_engine(case, cutoff=0.45)
+    eng.dist_emulate(world)
+    e2, f2 = eng.energy_forces()
+    assert eng.pair_kernel_in_use == 3
+    p2 = eng.cell_grid()["pairs"]
+    rep2 = eng.minimize(tol=10.0, max_iter=10)
+    x2 = eng.get_positions()
+    eng.close()
+    assert p1 == p2 and np.array_equal(e1, e2) and np.array_equal(f1, f2)
+    assert rep1["e_final"] == rep2["e_final"] and np.array_equal(x1, x2)
+
+
 def test_full_size_properties(built_lib):
     """BASELINE.json's genome-wide size (N = 2e5, 22 chromosomes, full term set), where the O(N^2) FP64
     oracle takes minutes: size-independent properties instead.  (1) The two independent exact kernels
