@@ -132,6 +132,7 @@ int mmm_destroy(mmm_handle h) {
                   h->d_fpair, h->epair_aliased ? nullptr : h->d_epair, h->d_facc, h->d_items, h->d_counter, h->d_epart, h->d_dpart, h->d_eterms, h->d_lb, h->d_xp,
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
                   h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs, h->d_v,
+                  h->d_cl_start, h->d_cl_of_bead, h->d_cl_by_chrom, h->d_cl_range, h->d_cl_cen, h->d_cl_force,
                   h->d_soa_sorted, h->d_tiles_sorted, h->d_stage_boxes, h->d_sort_table, h->d_items_cut, h->d_cut_npairs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -436,17 +437,21 @@ static int ensure_scratch(mmm_system* h) {
   // cut-off mode: the default forms run on the Newton-3 machinery over Morton-sorted tiles
   // (mmm_cutoff.cu), every other form on the cell-list gather kernel (mmm_cells.cu)
   const bool cut_n3 = mode == 3 && h->pair_kernel_pref != 1 && mmm_pair_n3_eligible(h);
-  const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0) + (cut_n3 ? 64 : 0);
+  // coarse-stage surrogate: CHB on cluster centroids instead of the exact same-chromosome pass
+  const bool chb_cl = mode == 3 && h->chb_surrogate && h->pp.chb_form == MMM_CHB_POLYNOMIAL;
+  const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0) + (cut_n3 ? 64 : 0) + (chb_cl ? 128 : 0);
   if (h->scratch_sig == sig) return MMM_OK;
   free_scratch(h);
   h->pair_mode = mode;
   h->cut_n3 = cut_n3;
+  h->chb_clusters = chb_cl;
   h->sort_age = 0;
   int rc;
+  if (chb_cl && h->nccl_comm) return mmm_fail(h, MMM_ERR_STATE, "the CHB cluster surrogate is single-GPU (coarse stage of the two-stage minimisation)");
   // cut-off mode with CHB on: an exact CHB-only pass runs beside the cell-list pass — the Newton-3
   // kernel over same-chromosome tile pairs for the polynomial form, the generic gather kernel else
-  const bool chb_n3 = mode == 3 && h->pp.chb_form == MMM_CHB_POLYNOMIAL;
-  const bool chb_gather = mode == 3 && h->pp.chb_form >= 0 && !chb_n3;
+  const bool chb_n3 = mode == 3 && h->pp.chb_form == MMM_CHB_POLYNOMIAL && !chb_cl;
+  const bool chb_gather = mode == 3 && h->pp.chb_form >= 0 && !chb_n3 && !chb_cl;
   h->n_items = 0;
   h->n3_items = 0;
   h->n_planes = 0;
@@ -505,6 +510,11 @@ static int ensure_scratch(mmm_system* h) {
     h->n_planes += 1;
     h->n_items += mmm_cells_energy_slots(h);
   }
+  if (chb_cl) {
+    if ((rc = mmm_chb_clusters_build(h))) return rc;
+    h->cl_item0 = h->n_items;
+    h->n_items += mmm_chb_clusters_blocks(h);
+  }
   if (h->n_items == 0) h->n_items = 1;
   if (h->n_planes > 0) {
     const size_t cnt = (size_t)h->n_planes * 3 * (size_t)h->npad;
@@ -533,7 +543,9 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
   // several GPUs: the energy slots of the other ranks' items must enter the all-reduce as zero bits
   if (h->nccl_comm) MMM_CUDA(h, cudaMemsetAsync(h->d_epair, 0, sizeof(double) * 4 * (size_t)h->n_items, h->stream));
   if (h->pair_mode == 3) {
-    if (h->pp.chb_form == MMM_CHB_POLYNOMIAL) {
+    if (h->chb_clusters) {
+      if ((rc = mmm_launch_chb_clusters(h, d_skip))) return rc;
+    } else if (h->pp.chb_form == MMM_CHB_POLYNOMIAL) {
       if ((rc = mmm_launch_pair_n3(h, d_skip, true))) return rc;
     } else if (h->pp.chb_form >= 0) {
       PairParams only_chb = h->pp;
@@ -675,6 +687,18 @@ int mmm_set_pair_kernel(mmm_handle h, int which) {
 }
 
 int mmm_pair_kernel_in_use(mmm_handle h) { return h ? h->pair_mode : 0; }
+
+int mmm_set_chb_surrogate(mmm_handle h, int on) {
+  if (!h) return MMM_ERR_ARG;
+  h->chb_surrogate = on != 0;
+  return MMM_OK;
+}
+
+int mmm_set_graph(mmm_handle h, int on) {
+  if (!h) return MMM_ERR_ARG;
+  h->no_graph = on == 0;
+  return MMM_OK;
+}
 
 int mmm_last_pair_kernel_ms(mmm_handle h, float* ms_out) {
   if (!h || !ms_out) return MMM_ERR_ARG;

@@ -27,6 +27,7 @@ struct AsmArgs {
   const int* bl_ptr; const int* bl_partner; const int* bl_flags; const double* bl_r0; const double* bl_k;
   const int* an_ptr; const int4* an_ijk; const double2* an_par;
   const signed char* s; const double* cstr;
+  const double* cl_force; const int* cl_of_bead;  // CHB cluster surrogate: force of the bead's cluster (or NULL)
   ExternalParams ep;
   double* g;
   double* epart;  // [blocks][6]: SC, LAM, CF, BOND, LOOP, ANGLE
@@ -79,6 +80,10 @@ __global__ void __launch_bounds__(kAsmBlock) k_assemble(const AsmArgs A) {
         fy += fp[(size_t)A.npad + i];
         fz += fp[2 * (size_t)A.npad + i];
       }
+    }
+    if (A.cl_force) {
+      const size_t c = (size_t)A.cl_of_bead[i];
+      fx += A.cl_force[3 * c]; fy += A.cl_force[3 * c + 1]; fz += A.cl_force[3 * c + 2];
     }
     const double xi = A.x[3 * i], yi = A.x[3 * i + 1], zi = A.x[3 * i + 2];
 
@@ -332,6 +337,8 @@ int mmm_launch_assemble(mmm_system* h, const int* d_skip) {
   A.bl_r0 = h->d_bl_r0; A.bl_k = h->d_bl_k;
   A.an_ptr = h->d_an_ptr; A.an_ijk = h->d_an_ijk; A.an_par = h->d_an_par;
   A.s = h->d_s; A.cstr = h->d_cstr;
+  A.cl_force = (h->pair_mode == 3 && h->chb_clusters) ? h->d_cl_force : nullptr;
+  A.cl_of_bead = h->d_cl_of_bead;
   A.ep = h->ep;
   A.g = h->d_g;
   A.epart = h->d_epart;

@@ -394,7 +394,7 @@ int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
   cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
   cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
   if (collect) h->ev_cursor++;
-  MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+  if (!h->capturing) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
 
   int* count = reinterpret_cast<int*>(h->d_sort_tmp);
   int* cursor = count + kMaxCodes;
@@ -430,7 +430,7 @@ int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip) {
   }
   h->launches += 6;
   MMM_CUDA(h, cudaGetLastError());
-  MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  if (!h->capturing) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
 }
 

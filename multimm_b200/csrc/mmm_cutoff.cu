@@ -115,30 +115,30 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __re
     if (e < n) atomicAdd(&s_cnt[(keys[e] >> shift) & (kDigits - 1)], 1);
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < kDigits; d += kSortThreads) table[(size_t)d * nblocks + blockIdx.x] = s_cnt[d];
+  for (int d = threadIdx.x; d < kDigits; d += kSortThreads) table[(size_t)blockIdx.x * kDigits + d] = s_cnt[d];
 }
 
-// exclusive scan of the (digit-major) table, in place; one block
-__global__ void __launch_bounds__(1024) k_sort_scan(int* __restrict__ table, int count, const int* __restrict__ skip) {
+// Exclusive scan of the digit x block counts in digit-major order (all blocks of digit 0, then digit
+// 1, ...), in place; one block, thread d owns digit d.  The table is stored block-major
+// (table[b * 1024 + d]) so that both sweeps over the blocks are coalesced across the threads.
+__global__ void __launch_bounds__(kDigits) k_sort_scan(int* __restrict__ table, int nblocks, const int* __restrict__ skip) {
   if (skip && *skip) return;
-  __shared__ int s_sum[1024];
-  const int t = threadIdx.x;
-  const int per = (count + 1023) / 1024;
-  const int lo = min(t * per, count), hi = min(lo + per, count);
-  int local = 0;
-  for (int q = lo; q < hi; ++q) local += table[q];
-  s_sum[t] = local;
+  __shared__ int s_sum[kDigits];
+  const int d = threadIdx.x;
+  int total = 0;
+  for (int b = 0; b < nblocks; ++b) total += table[(size_t)b * kDigits + d];
+  s_sum[d] = total;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int v = t >= o ? s_sum[t - o] : 0;
+  for (int o = 1; o < kDigits; o <<= 1) {  // Hillis-Steele inclusive scan of the digit totals
+    const int v = d >= o ? s_sum[d - o] : 0;
     __syncthreads();
-    s_sum[t] += v;
+    s_sum[d] += v;
     __syncthreads();
   }
-  int run = s_sum[t] - local;
-  for (int q = lo; q < hi; ++q) {
-    const int c = table[q];
-    table[q] = run;
+  int run = s_sum[d] - total;  // beads with a smaller digit
+  for (int b = 0; b < nblocks; ++b) {
+    const int c = table[(size_t)b * kDigits + d];
+    table[(size_t)b * kDigits + d] = run;
     run += c;
   }
 }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* _
   __syncthreads();
   // exclusive prefix over the warps, per digit
   for (int d = threadIdx.x; d < kDigits; d += kSortThreads) {
-    int run = table[(size_t)d * nblocks + blockIdx.x];
+    int run = table[(size_t)blockIdx.x * kDigits + d];
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
       const int c = s_cnt[w][d];
@@ -314,7 +314,7 @@ static int rebuild_order(mmm_system* h, const int* d_skip) {
   for (int pass = 0; pass < kPasses; ++pass) {
     const int shift = pass * kDigitBits;
     k_sort_hist<<<nblocks, kSortThreads, 0, h->stream>>>(kin, n, shift, h->d_sort_table, nblocks, d_skip);
-    k_sort_scan<<<1, 1024, 0, h->stream>>>(h->d_sort_table, kDigits * nblocks, d_skip);
+    k_sort_scan<<<1, kDigits, 0, h->stream>>>(h->d_sort_table, nblocks, d_skip);
     k_sort_scatter<<<nblocks, kSortThreads, 0, h->stream>>>(kin, iin, n, shift, h->d_sort_table, nblocks, kout, iout, d_skip);
     std::swap(kin, kout);
     std::swap(iin, iout);
@@ -338,7 +338,7 @@ int mmm_launch_pair_cutoff_n3(mmm_system* h, const int* d_skip) {
   cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
   cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
   if (collect) h->ev_cursor++;
-  MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+  if (!h->capturing) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
   // a converged minimisation skips every kernel (d_skip): the counter still advances, harmless
   if (h->sort_age <= 0 || h->sort_age >= kResortEvery) {
     if ((rc = rebuild_order(h, d_skip))) return rc;
@@ -352,9 +352,11 @@ int mmm_launch_pair_cutoff_n3(mmm_system* h, const int* d_skip) {
   h->launches += 2;
   MMM_CUDA(h, cudaGetLastError());
   if ((rc = mmm_launch_pair_n3_cut(h, d_skip))) return rc;
-  MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  if (!h->capturing) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
 }
+
+int mmm_cutoff_resort_period() { return kResortEvery; }
 
 int mmm_cutoff_read_grid(mmm_system* h, float* cell, int32_t* dim, float* origin) {
   CutGrid g;

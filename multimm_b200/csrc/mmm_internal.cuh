@@ -108,6 +108,9 @@ struct mmm_system {
   int sm_count = 148;
   std::string err;
   int64_t launches = 0;
+  bool capturing = false;          // a CUDA graph capture is in progress: no event records, no allocations
+  bool no_graph = false;           // mmm_set_graph(h, 0): plain launches in mmm_minimize (A/B timing)
+  int64_t launches_per_period = 0; // kernels in one replay of the captured period
 
   // parameters (host copies)
   PairParams pp{};
@@ -212,6 +215,17 @@ struct mmm_system {
   std::vector<int32_t> h_cut_iblk;     // i-block of every item of d_items_cut (slab boundaries of the sharded mode)
   double* d_cut_npairs = nullptr;      // [n_items_cut] pairs inside the cut-off
   int sort_age = 0;                    // evaluations since the Morton order was rebuilt (0: rebuild now)
+  // CHB on cluster centroids (mmm_chb_clusters.cu): coarse-stage surrogate, cut-off mode only
+  bool chb_surrogate = false;    // requested (mmm_set_chb_surrogate)
+  bool chb_clusters = false;     // in force for the current scratch
+  int n_clusters = 0;
+  int* d_cl_start = nullptr;     // [n_clusters + 1] first bead of every cluster
+  int* d_cl_of_bead = nullptr;   // [n] cluster of every bead
+  int* d_cl_by_chrom = nullptr;  // [n_clusters] clusters sorted by chromosome id
+  int2* d_cl_range = nullptr;    // [n_clusters] slots of by_chrom that hold the same chromosome
+  double* d_cl_cen = nullptr;    // [n_clusters][4] centroid, bead count
+  double* d_cl_force = nullptr;  // [n_clusters][3] force on every bead of the cluster
+  int64_t cl_item0 = 0;          // first d_epair item of the cluster pass
   int cells_plane = 0;           // plane of d_fpair the cell-list pass writes
   int64_t cells_item0 = 0;       // first d_epair item of the cell-list pass
 
@@ -256,6 +270,11 @@ int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip);  // sorted arrays 
 // mmm_cutoff.cu
 int mmm_launch_pair_cutoff_n3(mmm_system* h, const int* d_skip);
 int mmm_cutoff_read_grid(mmm_system* h, float* cell, int32_t* dim, float* origin);
+int mmm_cutoff_resort_period();
+// mmm_chb_clusters.cu
+int mmm_chb_clusters_build(mmm_system* h);
+int mmm_chb_clusters_blocks(const mmm_system* h);
+int mmm_launch_chb_clusters(mmm_system* h, const int* d_skip);
 // mmm_cells.cu
 int mmm_launch_pair_cutoff(mmm_system* h, const int* d_skip);
 int64_t mmm_cells_energy_slots(const mmm_system* h);

@@ -4,7 +4,8 @@
 //   epsilon = tol / max(1, rms |x_i|), stop when |g| / max(1,|x|) <= epsilon.
 //
 // No host round trip per iteration.  Every evaluation is the same kernel sequence
-//     k_apply -> k_prepare -> k_pair -> k_assemble -> k_dots -> k_decide
+//     k_apply -> k_prepare -> k_pair -> k_assemble -> k_dots (whose last block decides)
+// captured once as a CUDA graph and replayed
 // and all control flow (Armijo / Wolfe tests, step scaling, acceptance, convergence, history
 // rotation) lives in LbfgsState on the device.  The host enqueues batches of evaluations and
 // looks at one pinned int per batch; once `done` is set every kernel returns at its first
@@ -39,11 +40,25 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // One pass over x, g, gp, d and the valid history slots; y = g - gp is formed on the fly.
+struct DecideArgs {
+  LbfgsState* st;
+  const double* epair; int n_items;
+  const double* epart; int n_eblocks;
+  const double* dpart; int n_dblocks;
+  double* eterms;
+  unsigned* ticket;  // blocks of k_dots that have finished (last-block-done)
+};
+
+__device__ void decide(const DecideArgs& A);
+__device__ void decide_serial(LbfgsState* st, const double* s_val, double* eterms, double (*G)[MMM_LBFGS_M][MMM_LBFGS_M]);
+
+// decide != 0: the block that finishes last goes on to play liblbfgs on the sums (one launch less
+// per evaluation, which is what a small system's iteration time is made of).
 __global__ void __launch_bounds__(kDotBlock) k_dots(const LbfgsState* __restrict__ st, int64_t n3,
                                                     const double* __restrict__ x, const double* __restrict__ g,
                                                     const double* __restrict__ gp, const double* __restrict__ d,
                                                     const double* __restrict__ S, const double* __restrict__ Y,
-                                                    double* __restrict__ dpart) {
+                                                    double* __restrict__ dpart, const DecideArgs DA, const int decide_too) {
   if (st->done) return;
   __shared__ double s_red[kDotBlock / 32][MMM_NDOT];
   const int bound = st->bound;
@@ -85,23 +100,34 @@ __global__ void __launch_bounds__(kDotBlock) k_dots(const LbfgsState* __restrict
     for (int w = 0; w < kDotBlock / 32; ++w) s += s_red[w][q];
     dpart[(size_t)blockIdx.x * MMM_NDOT + q] = s;
   }
+  if (!decide_too) return;
+  __shared__ bool s_last;
+  __threadfence();  // this block's partials are visible before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(DA.ticket, 1u);
+    s_last = t == gridDim.x - 1;
+    if (s_last) *DA.ticket = 0u;  // ready for the next evaluation
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  decide(DA);
 }
 
-struct DecideArgs {
-  LbfgsState* st;
-  const double* epair; int n_items;
-  const double* epart; int n_eblocks;
-  const double* dpart; int n_dblocks;
-  double* eterms;
-};
-
-// Single block.  Warps reduce the partial sums in a fixed order, then thread 0 plays liblbfgs.
-__global__ void __launch_bounds__(256) k_decide(const DecideArgs A) {
+// One block (the last of k_dots).  Warps reduce the partial sums in a fixed order — independent of
+// which block happened to be last — then thread 0 plays liblbfgs on coefficients held in shared memory.
+__device__ void decide(const DecideArgs& A) {
   LbfgsState* st = A.st;
-  if (st->done) return;
   __shared__ double s_val[MMM_NUM_TERMS + MMM_NDOT];
+  __shared__ double s_G[3][M][M];  // Gss, Gsy, Gyy
+  constexpr int kWarps = kDotBlock / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int q = warp; q < MMM_NUM_TERMS + MMM_NDOT; q += 8) {
+  for (int q = threadIdx.x; q < 3 * M * M; q += kDotBlock) {
+    const int m = q / (M * M), r = (q / M) % M, c = q % M;
+    s_G[m][r][c] = m == 0 ? st->Gss[r][c] : (m == 1 ? st->Gsy[r][c] : st->Gyy[r][c]);
+  }
+  for (int q = warp; q < MMM_NUM_TERMS + MMM_NDOT; q += kWarps) {
     double acc = 0.0;
     if (q < 4) {
       for (int b = lane; b < A.n_items; b += 32) acc += A.epair[(size_t)b * 4 + q];
@@ -114,14 +140,24 @@ __global__ void __launch_bounds__(256) k_decide(const DecideArgs A) {
     if (lane == 0) s_val[q] = acc;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x == 0) decide_serial(st, s_val, A.eterms, s_G);
+  __syncthreads();
+  for (int q = threadIdx.x; q < 3 * M * M; q += kDotBlock) {
+    const int m = q / (M * M), r = (q / M) % M, c = q % M;
+    (m == 0 ? st->Gss[r][c] : (m == 1 ? st->Gsy[r][c] : st->Gyy[r][c])) = s_G[m][r][c];
+  }
+}
 
+__device__ void decide_serial(LbfgsState* st, const double* s_val, double* eterms, double (*G)[M][M]) {
+  double (*Gss)[M] = G[0];
+  double (*Gsy)[M] = G[1];
+  double (*Gyy)[M] = G[2];
   const double* D = s_val + MMM_NUM_TERMS;
   double f = 0.0;
   for (int t = 0; t < MMM_NUM_TERMS; ++t) {
     f += s_val[t];
     st->e_terms[t] = s_val[t];
-    A.eterms[t] = s_val[t];
+    eterms[t] = s_val[t];
   }
   st->evaluations++;
   const double ftol = 1e-4, wolfe = 0.9, min_step = 1e-20, max_step = 1e20;
@@ -191,14 +227,14 @@ __global__ void __launch_bounds__(256) k_decide(const DecideArgs A) {
     gs[l] = D[D_GS + l];
     gy[l] = D[D_GY + l];
     if (l == e || l >= bound_old) continue;
-    st->Gss[e][l] = st->Gss[l][e] = step * D[D_DS + l];
-    st->Gsy[e][l] = step * D[D_DY + l];  // s_e . y_l
-    st->Gsy[l][e] = D[D_YS + l];         // s_l . y_e
-    st->Gyy[e][l] = st->Gyy[l][e] = D[D_YY + l];
+    Gss[e][l] = Gss[l][e] = step * D[D_DS + l];
+    Gsy[e][l] = step * D[D_DY + l];  // s_e . y_l
+    Gsy[l][e] = D[D_YS + l];         // s_l . y_e
+    Gyy[e][l] = Gyy[l][e] = D[D_YY + l];
   }
-  st->Gss[e][e] = step * step * D[D_DD];
-  st->Gsy[e][e] = ys;
-  st->Gyy[e][e] = yy;
+  Gss[e][e] = step * step * D[D_DD];
+  Gsy[e][e] = ys;
+  Gyy[e][e] = yy;
   st->ys[e] = ys;
   gs[e] = step * D[D_GD];
   gy[e] = D[D_GYN];
@@ -217,7 +253,7 @@ __global__ void __launch_bounds__(256) k_decide(const DecideArgs A) {
   for (int q = 0; q < bound; ++q) {
     j = (j + M - 1) % M;
     double sd = cg * gs[j];
-    for (int l = 0; l < bound; ++l) sd += cs[l] * st->Gss[j][l] + cy[l] * st->Gsy[j][l];
+    for (int l = 0; l < bound; ++l) sd += cs[l] * Gss[j][l] + cy[l] * Gsy[j][l];
     alpha[j] = sd / st->ys[j];
     cy[j] -= alpha[j];
   }
@@ -226,7 +262,7 @@ __global__ void __launch_bounds__(256) k_decide(const DecideArgs A) {
   for (int l = 0; l < M; ++l) { cs[l] *= scale; cy[l] *= scale; }
   for (int q = 0; q < bound; ++q) {
     double yd = cg * gy[j];
-    for (int l = 0; l < bound; ++l) yd += cs[l] * st->Gsy[l][j] + cy[l] * st->Gyy[j][l];
+    for (int l = 0; l < bound; ++l) yd += cs[l] * Gsy[l][j] + cy[l] * Gyy[j][l];
     const double beta = yd / st->ys[j];
     cs[j] += alpha[j] - beta;
     j = (j + 1) % M;
@@ -302,18 +338,29 @@ __global__ void k_clear_flag(LbfgsState* st) { st->flag = APPLY_NONE; }
 
 int mmm_launch_dots_decide(mmm_system* h) {
   const int64_t n3 = 3 * h->n;
-  k_dots<<<h->n_dot_blocks, kDotBlock, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_gp, h->d_d, h->d_S,
-                                                       h->d_Y, h->d_dpart);
   DecideArgs A;
   A.st = h->d_lb;
   A.epair = h->d_epair; A.n_items = (int)h->n_items;
   A.epart = h->d_epart; A.n_eblocks = h->n_red_blocks;
   A.dpart = h->d_dpart; A.n_dblocks = h->n_dot_blocks;
   A.eterms = h->d_eterms;
-  k_decide<<<1, 256, 0, h->stream>>>(A);
-  h->launches += 2;
+  A.ticket = reinterpret_cast<unsigned*>(h->d_counter + 2);
+  k_dots<<<h->n_dot_blocks, kDotBlock, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_gp, h->d_d, h->d_S,
+                                                       h->d_Y, h->d_dpart, A, 1);
+  h->launches += 1;
   MMM_CUDA(h, cudaGetLastError());
   return MMM_OK;
+}
+
+// One L-BFGS evaluation as it is enqueued: apply -> prepare -> pair -> assemble -> dots (+ decide).
+static int enqueue_evaluation(mmm_system* h, int grid_apply) {
+  const int64_t n3 = 3 * h->n;
+  const int* d_done = &h->d_lb->done;
+  k_apply<<<grid_apply, 256, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_xp, h->d_gp, h->d_d, h->d_S, h->d_Y);
+  h->launches++;
+  int rc;
+  if ((rc = mmm_evaluate(h, d_done))) return rc;
+  return mmm_launch_dots_decide(h);
 }
 
 int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report* out) {
@@ -323,6 +370,7 @@ int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report
   MMM_CUDA(h, cudaMemsetAsync(h->d_xp, 0, sizeof(double) * n3, h->stream));
   MMM_CUDA(h, cudaMemsetAsync(h->d_gp, 0, sizeof(double) * n3, h->stream));
   MMM_CUDA(h, cudaMemsetAsync(h->d_d, 0, sizeof(double) * n3, h->stream));
+  MMM_CUDA(h, cudaMemsetAsync(h->d_counter + 2, 0, sizeof(int), h->stream));
 
   // epsilon = tol / max(1, sqrt(sum |x_i|^2 / N)), [OpenMM] LocalEnergyMinimizer::minimize
   // (one host read of |x|^2 before the loop starts; nothing is read back per iteration)
@@ -336,8 +384,9 @@ int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report
     // |x|^2 through the dot kernel: run it once with a dummy state
     MMM_CUDA(h, cudaMemcpyAsync(h->d_lb, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     MMM_CUDA(h, cudaMemsetAsync(h->d_g, 0, sizeof(double) * n3, h->stream));
+    DecideArgs none{};
     k_dots<<<h->n_dot_blocks, kDotBlock, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_gp, h->d_d,
-                                                         h->d_S, h->d_Y, h->d_dpart);
+                                                         h->d_S, h->d_Y, h->d_dpart, none, 0);
     h->launches++;
     std::vector<double> part((size_t)h->n_dot_blocks * MMM_NDOT);
     MMM_CUDA(h, cudaMemcpyAsync(part.data(), h->d_dpart, part.size() * sizeof(double), cudaMemcpyDeviceToHost,
@@ -352,22 +401,59 @@ int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report
   MMM_CUDA(h, cudaMemcpyAsync(h->d_lb, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   const int* d_done = &h->d_lb->done;
 
-  // first evaluation at x0
+  // first evaluation at x0 (also sizes every scratch buffer, so nothing allocates after this point)
   int rc;
   if ((rc = mmm_evaluate(h, d_done))) return rc;
   if ((rc = mmm_launch_dots_decide(h))) return rc;
 
   const int grid_apply = std::min<int64_t>((n3 + 255) / 256, (int64_t)h->sm_count * 8);
+  h->sort_age = 0;  // cut-off mode: the loop starts a fresh Morton-order period, with or without the graph
+
+  // One period of evaluations captured as a CUDA graph and replayed: the 6-7 small launches of an
+  // evaluation cost more host and launch latency than GPU time on a small system (configs[0]).  In
+  // cut-off mode a period is one life of the Morton order (kResortEvery evaluations, the first of
+  // which re-sorts).  Not with several GPUs (the collective stays a plain stream operation).
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int period = 1;
+  const bool use_graph = !h->nccl_comm && !h->no_graph;
+  if (use_graph) {
+    period = (h->pair_mode == 3 && h->cut_n3) ? mmm_cutoff_resort_period() : 1;
+    MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->capturing = true;
+    h->sort_age = 0;
+    const int64_t launches_before = h->launches;
+    cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    rc = MMM_OK;
+    if (ce == cudaSuccess) {
+      for (int q = 0; q < period && rc == MMM_OK; ++q) rc = enqueue_evaluation(h, grid_apply);
+      ce = cudaStreamEndCapture(h->stream, &graph);
+    }
+    h->capturing = false;
+    h->launches_per_period = h->launches - launches_before;
+    h->launches = launches_before;
+    h->sort_age = 0;  // the replayed period starts with a re-sort, exactly as captured
+    if (rc != MMM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      graph = nullptr;
+      gexec = nullptr;
+      period = 1;  // fall back to plain launches
+    }
+  }
+
   int batch = 4;
   LbfgsState fin;
   for (;;) {
     const auto tb0 = std::chrono::steady_clock::now();
     for (int b = 0; b < batch; ++b) {
-      k_apply<<<grid_apply, 256, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_xp, h->d_gp, h->d_d, h->d_S,
-                                                 h->d_Y);
-      h->launches++;
-      if ((rc = mmm_evaluate(h, d_done))) return rc;
-      if ((rc = mmm_launch_dots_decide(h))) return rc;
+      if (gexec) {
+        MMM_CUDA(h, cudaGraphLaunch(gexec, h->stream));
+        h->launches += h->launches_per_period;
+      } else if ((rc = enqueue_evaluation(h, grid_apply))) {
+        return rc;
+      }
     }
     MMM_CUDA(h, cudaMemcpyAsync(h->h_done, d_done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -381,6 +467,9 @@ int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report
     // collective), so the batch size may not depend on this rank's clock
     if (h->nccl_comm) batch = 8;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  h->sort_age = 0;  // whatever comes next re-sorts
   // a failed line search leaves a pending RESTORE (x <- xp)
   k_apply<<<grid_apply, 256, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_xp, h->d_gp, h->d_d, h->d_S, h->d_Y);
   k_clear_flag<<<1, 1, 0, h->stream>>>(h->d_lb);

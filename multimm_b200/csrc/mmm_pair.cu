@@ -333,7 +333,7 @@ int mmm_launch_pair_exact(mmm_system* h, const int* d_skip, const PairParams* pp
   cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
   cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
   if (collect) h->ev_cursor++;
-  if (timed) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+  if (timed && !h->capturing) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
   if (mmm_pair_fast_path_pp(A.pp)) {
     const int gk = (A.pp.scb_form >= 0 ? 1 : 0) | (A.pp.cob_form >= 0 ? 2 : 0);
     const bool chb = A.pp.chb_form >= 0;
@@ -344,6 +344,6 @@ int mmm_launch_pair_exact(mmm_system* h, const int* d_skip, const PairParams* pp
   }
   h->launches++;
   MMM_CUDA(h, cudaGetLastError());
-  if (timed) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  if (timed && !h->capturing) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
 }

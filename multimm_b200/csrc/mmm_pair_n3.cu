@@ -63,6 +63,9 @@ constexpr int kGroupUnroll = N3_GROUP_UNROLL;
 #ifndef N3_USE_F32X2
 #define N3_USE_F32X2 1
 #endif
+#ifndef N3_PACKED_NEAR
+#define N3_PACKED_NEAR 1  // tiles within the Gaussian range: packed f32x2 body (0: the scalar one)
+#endif
 #ifndef N3_MIN_BLOCKS
 #define N3_MIN_BLOCKS 2  // resident CTAs per SM the register budget is set for (2: 128 registers; 3: 80)
 #endif
@@ -189,6 +192,7 @@ struct EAcc {
   u64 ev2, chb2;  // packed partial sums of the f32x2 path
   float cnt;      // CUT: pairs inside the cut-off (reported through the CHB slot, which a CUT pass never uses)
   u64 cnt2;
+  u64 scb2, cob2;  // packed partial sums of the Gaussian-range packed path
 };
 
 // j-beads of a stage, laid out for the packed path: xy[j] = {-x, -x, -y, -y}, z[j] = {-z, -z}
@@ -244,6 +248,88 @@ __device__ __forceinline__ void pairs16_packed(const JDup sjd, const int a, cons
         const u64 bb = fma2(m3, r, fma2(kc4, r2, two2));
         const u64 nc = pk2(-c.chb_c, -c.chb_c);
         fs = fma2(nc, bb, fs);
+      }
+      u64 t;
+      t = fma2(fs, dx, pk2(I.fx[2 * m], I.fx[2 * m + 1])); unpk2(t, I.fx[2 * m], I.fx[2 * m + 1]);
+      t = fma2(fs, dy, pk2(I.fy[2 * m], I.fy[2 * m + 1])); unpk2(t, I.fy[2 * m], I.fy[2 * m + 1]);
+      t = fma2(fs, dz, pk2(I.fz[2 * m], I.fz[2 * m + 1])); unpk2(t, I.fz[2 * m], I.fz[2 * m + 1]);
+      ax = fma2(fs, dx, ax);
+      ay = fma2(fs, dy, ay);
+      az = fma2(fs, dz, az);
+    }
+    float lo, hi;
+    unpk2(ax, lo, hi); cx[k] = lo + hi;
+    unpk2(ay, lo, hi); cy[k] = lo + hi;
+    unpk2(az, lo, hi); cz[k] = lo + hi;
+  }
+}
+
+// Packed variant for tiles within the Gaussian range (and for every tile of a cut-off pass whose
+// cut-off is shorter than that range): EV + Gaussian block terms, optional same-chromosome CHB
+// (CHBM 1), optional truncation.  The label match of a block term is integer work on the ALU pipe
+// (2 LOP3 + 2 FSEL per term and register pair), everything else is packed; 3 MUFU per pair.
+template <int EVP, int GK, int CHBM, bool CUT>
+__device__ __forceinline__ void pairs16_packed_near(const float4* __restrict__ sj, const JDup sjd, const int a,
+                                                    const int b, const int jj0, IBeads& I, float (&cx)[2],
+                                                    float (&cy)[2], float (&cz)[2], EAcc& E, const N3Consts& c,
+                                                    const int* __restrict__ si4) {
+  const u64 rs2 = pk2(c.ev_rs, c.ev_rs), gc2 = pk2(c.g_c, c.g_c), mone2 = pk2(-1.0f, -1.0f);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int jl = (((jj0 + k) ^ a) << 2) | b;
+    const float4 nxy = sjd.xy[jl];
+    const float2 nz = sjd.z[jl];
+    const int tj = __float_as_int(sj[jl].w);
+    const float aj_scb = (GK & 1) ? c.a_scb[tj & 7] : 0.0f;
+    const float aj_cob = (GK & 2) ? c.a_cob[(tj >> 3) & 3] : 0.0f;
+    const u64 njx = pk2(nxy.x, nxy.y), njy = pk2(nxy.z, nxy.w), njz = pk2(nz.x, nz.y);
+    u64 ax = pk2(0.0f, 0.0f), ay = ax, az = ax;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const u64 dx = add2(I.x2[m], njx);
+      const u64 dy = add2(I.y2[m], njy);
+      const u64 dz = add2(I.z2[m], njz);
+      const u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+      float r2a, r2b;
+      unpk2(r2, r2a, r2b);
+      const u64 r = pk2(fast_sqrt(r2a), fast_sqrt(r2b));
+      const u64 q = fma2(rs2, r, r2);
+      float qa, qb;
+      unpk2(q, qa, qb);
+      const u64 wr = pk2(fast_rcp(qa), fast_rcp(qb));  // w / r
+      const u64 w = mul2(r, wr);
+      u64 wp = powi2<EVP>(w);
+      const u64 ge = mul2(r2, gc2);
+      float ga, gb;
+      unpk2(ge, ga, gb);
+      u64 g = pk2(fast_ex2(ga), fast_ex2(gb));
+      if (CUT) {
+        const u64 in2 = pk2(r2a < c.cut2 ? 1.0f : 0.0f, r2b < c.cut2 ? 1.0f : 0.0f);
+        wp = mul2(wp, in2);
+        g = mul2(g, in2);
+        E.cnt2 = add2(E.cnt2, in2);
+      }
+      E.ev2 = add2(E.ev2, wp);
+      u64 fs = mul2(wp, wr);
+      const int2 ti = *reinterpret_cast<const int2*>(si4 + 2 * m);  // labels of i-beads 2m, 2m + 1
+      const int xa = ti.x ^ tj, xb = ti.y ^ tj;
+      if (GK & 1) {
+        const u64 t = mul2(pk2((xa & 0x7) == 0 ? aj_scb : 0.0f, (xb & 0x7) == 0 ? aj_scb : 0.0f), g);
+        E.scb2 = add2(E.scb2, t);
+        fs = fma2(mone2, t, fs);
+      }
+      if (GK & 2) {
+        const u64 t = mul2(pk2((xa & 0x18) == 0 ? aj_cob : 0.0f, (xb & 0x18) == 0 ? aj_cob : 0.0f), g);
+        E.cob2 = add2(E.cob2, t);
+        fs = fma2(mone2, t, fs);
+      }
+      if (CHBM == 1) {
+        const u64 kc2 = pk2(c.chb_kc, c.chb_kc), one2 = pk2(1.0f, 1.0f);
+        const u64 t = fma2(kc2, r2, fma2(mone2, r, one2));  // kC r^2 + 1 - r
+        E.chb2 = fma2(r2, t, E.chb2);
+        const u64 kc4 = pk2(4.0f * c.chb_kc, 4.0f * c.chb_kc), two2 = pk2(2.0f, 2.0f), m3 = pk2(-3.0f, -3.0f);
+        const u64 bb = fma2(m3, r, fma2(kc4, r2, two2));
+        fs = fma2(pk2(-c.chb_c, -c.chb_c), bb, fs);
       }
       u64 t;
       t = fma2(fs, dx, pk2(I.fx[2 * m], I.fx[2 * m + 1])); unpk2(t, I.fx[2 * m], I.fx[2 * m + 1]);
@@ -370,12 +456,14 @@ __device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup
                                        const int b, IBeads& I, float (&out)[3], EAcc& E, const N3Consts& c,
                                        const int* __restrict__ si4, const int self_d) {
   constexpr bool kPacked = N3_USE_F32X2 && GK == 0 && !SELF && (EVP > 0 ? CHBM <= 1 : CHBM == 1);
+  constexpr bool kPackedNear = N3_USE_F32X2 && N3_PACKED_NEAR && GK != 0 && !SELF && EVP > 0 && CHBM <= 1;
   float s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;  // saved group (g even)
   float p0x = 0.f, p0y = 0.f, p0z = 0.f, p1x = 0.f, p1y = 0.f, p1z = 0.f;  // registers 0,1 after level "2"
 #pragma unroll kGroupUnroll
   for (int g = 0; g < 4; ++g) {
     float cx[2], cy[2], cz[2];
     if constexpr (kPacked) pairs16_packed<EVP, CHBM, CUT>(sjd, a, b, 2 * g, I, cx, cy, cz, E, c);
+    else if constexpr (kPackedNear) pairs16_packed_near<EVP, GK, CHBM, CUT>(sj, sjd, a, b, 2 * g, I, cx, cy, cz, E, c, si4);
     else pairs16<EVP, GK, CHBM, SELF, CUT>(sj, a, b, 2 * g, I, cx, cy, cz, E, c, si4, self_d);
     if (!WANT_J) continue;
     if ((g & 1) == 0) {
@@ -553,7 +641,7 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
         const int self_base = (int)(ibase + iw - (int64_t)js * N3_JB);
         EAcc E;
         E.ev = E.scb = E.cob = E.chb = E.cnt = 0.0f;
-        E.ev2 = E.chb2 = E.cnt2 = pk2(0.0f, 0.0f);
+        E.ev2 = E.chb2 = E.cnt2 = E.scb2 = E.cob2 = pk2(0.0f, 0.0f);
 
         if (!i_all_pad) {
           // Classify the stage's 8 tiles at once: lane s < 8 classifies tile s against this warp's
@@ -613,6 +701,8 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
           float lo, hi;
           unpk2(E.ev2, lo, hi); E.ev += lo + hi;
           unpk2(E.chb2, lo, hi); E.chb += lo + hi;
+          if (GK & 1) { unpk2(E.scb2, lo, hi); E.scb += lo + hi; }
+          if (GK & 2) { unpk2(E.cob2, lo, hi); E.cob += lo + hi; }
           if (CUT) { unpk2(E.cnt2, lo, hi); E.chb = E.cnt + lo + hi; }
         }
         const double wgt = diag ? 0.5 : 1.0;
@@ -839,7 +929,7 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   cudaEvent_t ea = collect ? h->ev_pool[2 * h->ev_cursor] : h->ev_a;
   cudaEvent_t eb = collect ? h->ev_pool[2 * h->ev_cursor + 1] : h->ev_b;
   if (collect) h->ev_cursor++;
-  if (timed) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
+  if (timed && !h->capturing) MMM_CUDA(h, cudaEventRecord(ea, h->stream));
   const bool chb = p.chb_form >= 0;
   // one launch for this rank's share of the items; in emulation every rank's share in turn
   const int r0 = h->dist_emulate ? 0 : h->dist_rank, r1 = h->dist_emulate ? h->dist_world : h->dist_rank + 1;
@@ -853,7 +943,7 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
     h->launches++;
   }
   MMM_CUDA(h, cudaGetLastError());
-  if (timed) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
+  if (timed && !h->capturing) MMM_CUDA(h, cudaEventRecord(eb, h->stream));
   return MMM_OK;
 }
 

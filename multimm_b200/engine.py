@@ -234,6 +234,15 @@ class Engine:
         """0 = automatic (Newton-3 kernel for the default forms), 1 = always the gather kernel."""
         self._ck(self._lib.mmm_set_pair_kernel(self._h, int(which)))
 
+    def set_chb_surrogate(self, on: bool):
+        """Cut-off mode only: CHB between cluster centroids instead of the exact same-chromosome pass
+        (coarse stage of the two-stage minimisation; not the reference's potential)."""
+        self._ck(self._lib.mmm_set_chb_surrogate(self._h, int(bool(on))))
+
+    def set_graph(self, on: bool):
+        """minimize(): replay a captured CUDA graph per evaluation (default) or launch kernel by kernel."""
+        self._ck(self._lib.mmm_set_graph(self._h, int(bool(on))))
+
     @property
     def pair_kernel_in_use(self) -> int:
         """0 none, 1 gather, 2 Newton-3, 3 cut-off cell list (kernel of the last evaluation)."""

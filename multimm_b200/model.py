@@ -286,8 +286,12 @@ class MultiMM:
             # 20 000); whatever it leaves undone the exact stage finishes.
             cap = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
             self.engine.set_cutoff(coarse)
+            # CHB cannot be truncated; the coarse stage evaluates it on cluster centroids (O(N)) unless told
+            # otherwise — the exact stage below restores the reference's potential
+            self.engine.set_chb_surrogate(str(getattr(a, "MIN_COARSE_CHB", "clusters")).lower() != "exact")
             self.coarse_report = self.engine.minimize(tol=tol, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
             self.engine.set_cutoff(0.0)
+            self.engine.set_chb_surrogate(False)
             self.timings["coarse_iterations"] = int(self.coarse_report["iterations"])
             self.timings["coarse_seconds"] = float(self.coarse_report["wall_seconds"])
         self.report = self.engine.minimize(tol=tol, max_iter=max_iter)

@@ -37,13 +37,24 @@ with tempfile.TemporaryDirectory() as tmp:
         eng.evaluate_timed(5, flush_l2=False)
         tot, pair = eng.evaluate_timed(40, flush_l2=False)
         out[name] = dict(ms_per_eval=tot / 40, cut_pass_ms=pair / 40, pairs_in_cutoff=eng.cell_grid()["pairs"])
-    # two-stage minimisation (MIN_COARSE_CUTOFF): coarse stage on the truncated potential, exact stage after
+    # the same with CHB on cluster centroids (coarse-stage surrogate)
     eng.set_pair_kernel(0)
-    eng.set_positions(x0)
-    t0 = time.perf_counter()
-    rep_c = eng.minimize(tol=10.0, max_iter=20000)
-    eng.set_cutoff(0.0)
-    rep_e = eng.minimize(tol=10.0, max_iter=0)
-    out["two_stage"] = dict(total_s=time.perf_counter() - t0, coarse=rep_c, exact=rep_e)
+    eng.set_chb_surrogate(True)
+    eng.set_positions(x1)
+    eng.evaluate_timed(5, flush_l2=False)
+    tot, pair = eng.evaluate_timed(40, flush_l2=False)
+    out["n3_sorted_tiles_relaxed_chb_clusters"] = dict(ms_per_eval=tot / 40, cut_pass_ms=pair / 40)
+    # two-stage minimisation (MIN_COARSE_CUTOFF): coarse stage on the truncated potential, exact stage after
+    for name, surrogate in (("two_stage_chb_clusters", True), ("two_stage_chb_exact", False)):
+        eng.set_cutoff(rc)
+        eng.set_chb_surrogate(surrogate)
+        eng.set_positions(x0)
+        t0 = time.perf_counter()
+        rep_c = eng.minimize(tol=10.0, max_iter=20000)
+        eng.set_cutoff(0.0)
+        eng.set_chb_surrogate(False)
+        rep_e = eng.minimize(tol=10.0, max_iter=0)
+        out[name] = dict(total_s=time.perf_counter() - t0, coarse=rep_c, exact=rep_e)
+        print(json.dumps({name: out[name]}), flush=True)
     m.close()
 print(json.dumps(out))

@@ -378,3 +378,65 @@ def test_errors(built_lib):
     with pytest.raises(ValueError):
         eng.set_loops([0], [5], [0.1], [1.0], form=9)
     eng.close()
+
+
+@pytest.mark.parametrize("cutoff", [0.0, 0.45])
+def test_graph_replay_is_bit_identical_to_plain_launches(built_lib, cutoff):
+    """mmm_minimize replays a captured CUDA graph per evaluation (per Morton-order period in cut-off
+    mode); with the graph switched off it launches kernel by kernel.  Same kernels, same order, same
+    arguments: the trajectories are the same bits, and so is the launch count."""
+    case = make_case(3000, n_chrom=2, seed=55)
+    out = []
+    for graph in (True, False):
+        eng = to_engine(case, cutoff=cutoff)
+        eng.set_graph(graph)
+        n0 = eng.launch_count
+        rep = eng.minimize(tol=10.0, max_iter=60)
+        out.append((rep["e_final"], rep["evaluations"], rep["iterations"], eng.get_positions()))
+        eng.close()
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1] and out[0][2] == out[1][2]
+    assert np.array_equal(out[0][3], out[1][3])
+
+
+def test_chb_cluster_surrogate(built_lib):
+    """Coarse-stage surrogate (cut-off mode, opt-in): CHB between cluster centroids.  (1) close to the
+    exact same-chromosome sum (the term is smooth: a few per cent at most on a compact structure);
+    (2) a proper potential: its force is the gradient of its energy (central differences along a random
+    direction); (3) switching it off restores the exact pass bit for bit; (4) exact mode ignores it."""
+    case = make_case(6000, n_chrom=3, seed=91, terms=("EV", "CHB"), chb_de=5.0)
+    eng = to_engine(case, cutoff=0.4)
+    e_exact, f_exact = eng.energy_forces()
+    eng.set_chb_surrogate(True)
+    e_s, f_s = eng.energy_forces()
+    assert abs(e_s[3] - e_exact[3]) <= 0.05 * abs(e_exact[3]) and e_s[3] != e_exact[3]
+    assert e_s[0] == e_exact[0]  # the truncated EV pass is untouched
+    rng = np.random.default_rng(3)
+    d = rng.normal(size=case["x"].shape)
+    d /= np.linalg.norm(d)
+    h = 1e-4
+    eng.set_positions(case["x"] + h * d)
+    ep = eng.energy_forces(want_forces=False)[0][3]
+    eng.set_positions(case["x"] - h * d)
+    em = eng.energy_forces(want_forces=False)[0][3]
+    # CHB part of the force along d: total force minus the (identical) EV part
+    eng.set_positions(case["x"])
+    f_chb_s = f_s - (f_exact - _chb_only_forces(case))
+    slope = -(ep - em) / (2 * h)
+    assert abs(slope - float((f_chb_s * d).sum())) <= 1e-4 * max(abs(slope), 1.0), (slope, float((f_chb_s * d).sum()))
+    eng.set_chb_surrogate(False)
+    e_back, f_back = eng.energy_forces()
+    assert np.array_equal(e_back, e_exact) and np.array_equal(f_back, f_exact)
+    eng.set_cutoff(0.0)
+    eng.set_chb_surrogate(True)
+    e_nocut, _ = eng.energy_forces()
+    eng.close()
+    e_ref, _ = O.energy_forces(to_oracle(case), case["x"])
+    assert abs(e_nocut[3] - e_ref[3]) <= E_TOL * abs(e_ref[3])  # exact mode: the reference's CHB, always
+
+
+def _chb_only_forces(case):
+    """Exact CHB forces of the case from the oracle (FP64)."""
+    only = dict(case)
+    only["ev"] = None
+    _, f = O.energy_forces(to_oracle(only), case["x"])
+    return f
