@@ -199,6 +199,14 @@ int mmm_md_run(mmm_handle h, int64_t n_steps, mmm_md_report *out);
 /* Mean of the full N x N distance matrix at the current positions (np.mean(cdist(V, V)),
  * plots.py:663-664) without materialising it. */
 int mmm_mean_pair_distance(mmm_handle h, double *mean_out);
+/* Block means of the contact map get_heatmap draws (plots.py:540-561: 1 / (d + 1)^(2/3) per bead pair,
+ * log1p if log_scale) over bins x bins blocks of consecutive beads (edges as np.linspace(0, n, bins + 1)
+ * .astype(int)), for ANY (n, 3) coordinate array — no handle: the structures the report reads back from
+ * .cif files are shorter than N_BEADS (HETATM rows dropped, utils.py:184-190).  The N x N matrix never
+ * exists, which lifts the reference's N < 50 000 limit (model.py:1095-1104).  mean_dist_out (may be NULL):
+ * np.mean(cdist(V, V)) from the same pass. */
+int mmm_contact_map(int device, const double *xyz, int64_t n, int bins, int log_scale, double *map_out,
+                    double *mean_dist_out);
 
 /* ---- one system on several GPUs of one box (exact mode only) -------------------------------- */
 /* The reference has no multi-GPU path (DeviceIndex is never set, model.py:862-876).  Here the

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 
-def mean_pair_distance_host(V: np.ndarray, block: int = 2048) -> float:
+def mean_pair_distance_host(V: np.ndarray, block: int = 256) -> float:
     n = len(V)
     total = 0.0
     for a in range(0, n, block):
@@ -37,7 +37,33 @@ def local_rg(V: np.ndarray, window: int) -> np.ndarray:
     return np.sqrt(np.maximum(var, 0.0))
 
 
-def analyze_structure(V, save_path, name="structure", engine=None) -> dict:
+CONTACT_BINS = 1000  # block-mean contact map saved with every report (the N x N matrix never exists)
+
+
+def device_pair_stats(V, bins: int, device: int = 0, log_scale: bool = True):
+    """(B x B block-mean contact map, np.mean(cdist(V, V))) of ANY (n, 3) array on the GPU
+    (csrc/mmm_analysis.cu: mmm_contact_map), one pass over the N^2 pairs in FP64."""
+    import ctypes as C
+
+    from . import _lib
+
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    n = len(V)
+    bins = max(1, min(int(bins), n))
+    out = np.empty((bins, bins), dtype=np.float64)
+    mean = C.c_double()
+    lib = _lib.load()
+    rc = lib.mmm_contact_map(int(device), V.ctypes.data_as(C.c_void_p), n, bins, int(bool(log_scale)),
+                             out.ctypes.data_as(C.c_void_p), C.byref(mean))
+    if rc != 0:
+        raise _lib.Error(rc, lib.mmm_last_error(None).decode() or "CUDA error: contact-map pass failed")
+    return out, float(mean.value)
+
+
+def analyze_structure(V, save_path, name="structure", engine=None, device=None) -> dict:
+    """`device` (a CUDA device index): the O(N^2) quantities — the mean pair distance of the report and
+    the block-mean contact map (saved as <name>_contact_map.npy; the heat-map the reference draws only
+    below 5e4 beads, model.py:1095-1104) — come from one pass on the GPU, for any number of rows of V."""
     V = np.asarray(V, dtype=np.float64)
     V = V[np.isfinite(V).all(axis=1)]
     n = len(V)
@@ -48,7 +74,10 @@ def analyze_structure(V, save_path, name="structure", engine=None) -> dict:
     Vc = V - r_cm
     rg = np.sqrt(np.mean(np.sum(Vc ** 2, axis=1)))
     ree = np.linalg.norm(V[-1] - V[0])
-    if engine is not None:
+    if device is not None:
+        cmap, mean_dist = device_pair_stats(V, CONTACT_BINS, device=device)
+        np.save(os.path.join(base, f"{name}_contact_map.npy"), cmap)
+    elif engine is not None and engine.n == n:
         engine.set_positions(V)
         mean_dist = engine.mean_pair_distance()
     else:

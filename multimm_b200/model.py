@@ -286,9 +286,10 @@ class MultiMM:
             # 20 000); whatever it leaves undone the exact stage finishes.
             cap = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
             self.engine.set_cutoff(coarse)
-            # CHB cannot be truncated; the coarse stage evaluates it on cluster centroids (O(N)) unless told
-            # otherwise — the exact stage below restores the reference's potential
-            self.engine.set_chb_surrogate(str(getattr(a, "MIN_COARSE_CHB", "clusters")).lower() != "exact")
+            # CHB cannot be truncated: the coarse stage carries its exact same-chromosome pass, or (opt-in,
+            # MIN_COARSE_CHB = clusters) evaluates it on cluster centroids — cheaper per evaluation, but the
+            # exact stage below may then have more left to do (profiles/r02_cutoff_mode.md)
+            self.engine.set_chb_surrogate(str(getattr(a, "MIN_COARSE_CHB", "exact")).lower() == "clusters")
             self.coarse_report = self.engine.minimize(tol=tol, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
             self.engine.set_cutoff(0.0)
             self.engine.set_chb_surrogate(False)
@@ -373,12 +374,11 @@ class MultiMM:
         todo = [("initial_structure", "metadata/MultiMM_init.cif"), ("minimized_structure", "model/MultiMM_minimized.cif")]
         if self.args.SIM_RUN_MD:
             todo.append(("structure_afterMD", "model/MultiMM_afterMD.cif"))
-        x_now = self.engine.get_positions()
         for name, rel in todo:
-            V = cif.read_cif_coordinates(self.save_path + rel, include_hetatm=False)  # get_coordinates_cif
-            eng = self.engine if len(V) == self.args.N_BEADS else None
-            analysis.analyze_structure(V, self.save_path, name=name, engine=eng)
-        self.engine.set_positions(x_now)
+            # get_coordinates_cif keeps ATOM rows only (utils.py:184-190), so V is shorter than N_BEADS
+            # (the chromosome-end beads are HETATM): the device pass takes any number of rows
+            V = cif.read_cif_coordinates(self.save_path + rel, include_hetatm=False)
+            analysis.analyze_structure(V, self.save_path, name=name, device=self.device)
 
     def save_args_to_txt(self, filename):
         """utils.py:733-742."""

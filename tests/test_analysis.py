@@ -69,3 +69,20 @@ def test_contact_map_block_means_never_need_the_full_matrix():
             edges = np.linspace(0, 301, b + 1).astype(int)
             ref = np.array([[full[edges[p]:edges[p + 1], edges[q]:edges[q + 1]].mean() for q in range(b)] for p in range(b)])
             assert cg.shape == (b, b) and np.allclose(cg, ref, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_device_contact_map_matches_host(built_lib):
+    """Block-mean contact map + mean pair distance in one device pass (mmm_contact_map) against the
+    host restatement of get_heatmap (plots.py:540-561), for an array whose length is no multiple of
+    anything (the report reads back CIFs without their HETATM rows)."""
+    from multimm_b200 import analysis
+
+    rng = np.random.default_rng(5)
+    V = np.cumsum(rng.normal(0.0, 0.6, size=(3001, 3)), axis=0)
+    for bins, log_scale in ((37, True), (3001, True), (64, False)):
+        got, mean = analysis.device_pair_stats(V, bins, device=0, log_scale=log_scale)
+        want = analysis.contact_map(V, log_scale=log_scale, bins=None if bins == len(V) else bins)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max() + 1e-13
+        assert abs(mean - analysis.mean_pair_distance_host(V)) <= 1e-12 * mean

@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _rank(rank, world, port, q):
+def _rank(rank, world, port, q, cutoff=0.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import torch
@@ -22,10 +22,11 @@ def _rank(rank, world, port, q):
     box = [Engine.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     case = make_case(20000, n_chrom=5, seed=3)
-    eng = to_engine(case, device=rank)
+    eng = to_engine(case, device=rank, cutoff=cutoff)
     eng.dist_init(rank, world, box[0])
     e, f = eng.energy_forces()
     rep = eng.minimize(tol=10.0, max_iter=20)
+    rep["exchange_ms"] = eng.last_collective_ms
     x = eng.get_positions()
     eng.close()
     dist.barrier()
@@ -33,7 +34,10 @@ def _rank(rank, world, port, q):
     q.put((rank, e, f, rep, x))
 
 
-def test_two_gpus_one_system(built_lib):
+@pytest.mark.parametrize("cutoff", [0.0, 0.45])
+def test_two_gpus_one_system(built_lib, cutoff):
+    """cutoff = 0: the exact pair work dealt round-robin; cutoff > 0: the Morton-sorted order cut into
+    one slab per GPU (CHB's exact pass still round-robin).  One all-reduce per evaluation either way."""
     import torch
     import torch.multiprocessing as mp
 
@@ -42,7 +46,7 @@ def test_two_gpus_one_system(built_lib):
     from common import make_case, to_engine
 
     case = make_case(20000, n_chrom=5, seed=3)
-    eng = to_engine(case, device=0)
+    eng = to_engine(case, device=0, cutoff=cutoff)
     e0, f0 = eng.energy_forces()
     rep0 = eng.minimize(tol=10.0, max_iter=20)
     x0 = eng.get_positions()
@@ -50,7 +54,7 @@ def test_two_gpus_one_system(built_lib):
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank, args=(r, 2, 29741, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank, args=(r, 2, 29741 + (1 if cutoff > 0 else 0), q, cutoff)) for r in range(2)]
     for p in procs:
         p.start()
     got = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
@@ -61,6 +65,7 @@ def test_two_gpus_one_system(built_lib):
         assert np.array_equal(e, e0) and np.array_equal(f, f0)
         assert rep["e_final"] == rep0["e_final"] and rep["evaluations"] == rep0["evaluations"]
         assert np.array_equal(x, x0)
+        assert rep["exchange_ms"] > 0.0  # the exchange step ran and was timed
 
 
 def test_ensemble_is_dealt_to_two_gpus(built_lib, tmp_path):
