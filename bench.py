@@ -481,6 +481,8 @@ def run_ours(opt):
                         exchange="one NCCL all-reduce (uint64 sum) of the fixed-point force planes and the per-item energy "
                         "slots; CUDA events around it on the engine's stream, last evaluation.  A rank's figure includes its "
                         "wait for the slowest rank's pair kernel: the smallest over ranks is the collective itself",
+                        work_queue=("one queue for all GPUs (ticket counters in rank 0's memory, CUDA IPC, system-scope "
+                                    "atomics over NVLink)" if ms_.engine.dist_queue_mode else "static round-robin dealing"),
                         build_seconds=time.perf_counter() - t0,
                         single_gpu_reference="profiles/: 1 GPU runs the same system in ms_per_evaluation x speed-up")
             ms_.close()

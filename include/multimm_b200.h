@@ -221,6 +221,10 @@ int mmm_dist_init(mmm_handle h, int rank, int world, const void *unique_id, int 
 /* Single-GPU emulation of the sharding (tests): the shares of all `world` ranks are run one
  * after another on this handle's GPU into the same accumulators. */
 int mmm_dist_emulate(mmm_handle h, int world);
+/* 1 if the ranks draw their work items from ONE queue (two ticket counters in rank 0's memory, opened by
+ * the other ranks through CUDA IPC, advanced with system-scope atomics over NVLink — a slower GPU simply
+ * takes fewer items), 0 if the items are dealt round-robin (IPC unavailable, or MMM_DIST_STATIC=1). */
+int mmm_dist_queue_mode(mmm_handle h);
 /* Milliseconds the exchange step of the most recent evaluation took on this rank (CUDA events on
  * the handle's stream around the all-reduce; includes the wait for the slowest rank).  0 without a
  * communicator. */

@@ -133,7 +133,8 @@ int mmm_destroy(mmm_handle h) {
                   h->d_gp, h->d_d, h->d_S, h->d_Y, h->d_keys, h->d_order, h->d_keys_tmp, h->d_order_tmp,
                   h->d_pos4_sorted, h->d_cell_start, h->d_sort_tmp, h->d_cell_grid, h->d_cell_npairs, h->d_v,
                   h->d_cl_start, h->d_cl_of_bead, h->d_cl_by_chrom, h->d_cl_range, h->d_cl_cen, h->d_cl_force,
-                  h->d_soa_sorted, h->d_tiles_sorted, h->d_stage_boxes, h->d_sort_table, h->d_items_cut, h->d_cut_npairs};
+                  h->d_soa_sorted, h->d_tiles_sorted, h->d_stage_boxes, h->d_sort_table, h->d_items_cut, h->d_cut_npairs,
+                  h->d_cut_eacc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   mmm_dist_destroy(h);
@@ -428,6 +429,7 @@ static void free_scratch(mmm_system* h) {
   if (h->d_items) { cudaFree(h->d_items); h->d_items = nullptr; }
   if (h->d_items_cut) { cudaFree(h->d_items_cut); h->d_items_cut = nullptr; }
   if (h->d_cut_npairs) { cudaFree(h->d_cut_npairs); h->d_cut_npairs = nullptr; }
+  if (h->d_cut_eacc) { cudaFree(h->d_cut_eacc); h->d_cut_eacc = nullptr; }
   h->scratch_sig = -1;
 }
 
@@ -439,11 +441,15 @@ static int ensure_scratch(mmm_system* h) {
   const bool cut_n3 = mode == 3 && h->pair_kernel_pref != 1 && mmm_pair_n3_eligible(h);
   // coarse-stage surrogate: CHB on cluster centroids instead of the exact same-chromosome pass
   const bool chb_cl = mode == 3 && h->chb_surrogate && h->pp.chb_form == MMM_CHB_POLYNOMIAL;
-  const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0) + (cut_n3 ? 64 : 0) + (chb_cl ? 128 : 0);
+  // pair_kernel_pref 2: the CTA-level CUT variant instead of the one-warp-per-item kernel (A/B timing)
+  const bool cut_warp = cut_n3 && h->pair_kernel_pref != 2;
+  const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0) + (cut_n3 ? 64 : 0) + (chb_cl ? 128 : 0) +
+                  (cut_warp ? 256 : 0);
   if (h->scratch_sig == sig) return MMM_OK;
   free_scratch(h);
   h->pair_mode = mode;
   h->cut_n3 = cut_n3;
+  h->cut_warp = cut_warp;
   h->chb_clusters = chb_cl;
   h->sort_age = 0;
   int rc;
@@ -457,7 +463,10 @@ static int ensure_scratch(mmm_system* h) {
   h->n_planes = 0;
   h->nchunk = 1;
   std::vector<int2> items_cut;
-  if (cut_n3) mmm_n3_build_items(h, items_cut, false);
+  if (cut_warp) mmm_cut_warp_build_items(h, items_cut);
+  else if (cut_n3) mmm_n3_build_items(h, items_cut, false);
+  // energy slots of the cut-off pass: one per item (CTA-level kernel) or one per rank (warp kernel)
+  h->n_cut_slots = cut_warp ? h->dist_world : (int)items_cut.size();
   if (mode == 2 || chb_n3) {
     // Newton-3: fixed-point force planes + work-item table
     std::vector<int2> items;
@@ -472,7 +481,7 @@ static int ensure_scratch(mmm_system* h) {
   if (mode == 2 || chb_n3 || cut_n3) {
     // several GPUs: the per-item energy slots live behind the force planes in the same allocation,
     // so that ONE all-reduce (uint64 sum) covers both (mmm_dist.cu)
-    const size_t tail = h->nccl_comm ? 4 * ((size_t)h->n3_items + items_cut.size()) : 0;
+    const size_t tail = h->nccl_comm ? 4 * ((size_t)h->n3_items + (size_t)h->n_cut_slots) : 0;
     if ((rc = dev_alloc(h, &h->d_facc, 3 * (size_t)h->npad + tail))) return rc;
     MMM_CUDA(h, cudaMemsetAsync(h->d_facc, 0, sizeof(unsigned long long) * (3 * (size_t)h->npad + tail), h->stream));
   }
@@ -500,10 +509,14 @@ static int ensure_scratch(mmm_system* h) {
     if ((rc = dev_alloc(h, &h->d_items_cut, items.size()))) return rc;
     MMM_CUDA(h, cudaMemcpyAsync(h->d_items_cut, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
-    if ((rc = dev_alloc(h, &h->d_cut_npairs, items.size()))) return rc;
-    MMM_CUDA(h, cudaMemsetAsync(h->d_cut_npairs, 0, sizeof(double) * items.size(), h->stream));
+    if ((rc = dev_alloc(h, &h->d_cut_npairs, (size_t)h->n_cut_slots))) return rc;
+    MMM_CUDA(h, cudaMemsetAsync(h->d_cut_npairs, 0, sizeof(double) * (size_t)h->n_cut_slots, h->stream));
+    if (cut_warp) {
+      if ((rc = dev_alloc(h, &h->d_cut_eacc, 4))) return rc;
+      MMM_CUDA(h, cudaMemsetAsync(h->d_cut_eacc, 0, sizeof(unsigned long long) * 4, h->stream));
+    }
     h->cells_item0 = h->n_items;
-    h->n_items += h->n_items_cut;
+    h->n_items += h->n_cut_slots;
   } else if (mode == 3) {
     h->cells_plane = h->n_planes;
     h->cells_item0 = h->n_items;
@@ -681,7 +694,7 @@ int64_t mmm_launch_count(mmm_handle h) { return h ? h->launches : 0; }
 
 int mmm_set_pair_kernel(mmm_handle h, int which) {
   if (!h) return MMM_ERR_ARG;
-  REQUIRE(h, which == 0 || which == 1, "mmm_set_pair_kernel: 0 = automatic, 1 = gather kernel");
+  REQUIRE(h, which >= 0 && which <= 2, "mmm_set_pair_kernel: 0 = automatic, 1 = gather kernels, 2 = CTA-level cut-off kernel");
   h->pair_kernel_pref = which;
   return MMM_OK;
 }

@@ -458,7 +458,7 @@ int mmm_get_cell_grid(mmm_handle h, float* cell_out, int32_t* dim_out, float* or
     int rc = mmm_cutoff_read_grid(h, cell_out, dim_out, origin_out);
     if (rc) return rc;
     if (pairs_in_cutoff) {
-      std::vector<double> per_item((size_t)h->n_items_cut);
+      std::vector<double> per_item((size_t)h->n_cut_slots);
       MMM_CUDA(h, cudaMemcpyAsync(per_item.data(), h->d_cut_npairs, per_item.size() * sizeof(double),
                                   cudaMemcpyDeviceToHost, h->stream));
       MMM_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -18,6 +18,7 @@
 // GPU into the same accumulators: the sharding logic is testable without a second GPU.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mmm_internal.cuh"
@@ -29,6 +30,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
@@ -44,6 +46,7 @@ NcclApi* nccl() {
   api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
   api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+  api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
   api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
   api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
@@ -71,7 +74,81 @@ int mmm_dist_allreduce(mmm_system* h) {
   return MMM_OK;
 }
 
+// One work queue for all GPUs: two ticket counters in rank 0's memory, opened by every other rank
+// through CUDA IPC and advanced with system-scope atomics over NVLink.  The Newton-3 kernel of every
+// rank draws its items from the same counter, so a GPU that runs slower (clock, power cap) simply takes
+// fewer items — no rank waits in the all-reduce for a straggler.  Which rank runs which item does not
+// matter to the result (integer force accumulation, one writer per energy slot).
+static int setup_global_queue(mmm_system* h, NcclApi* a) {
+  h->d_gqueue = nullptr;
+  h->gqueue_owner = false;
+  const char* off = getenv("MMM_DIST_STATIC");
+  if (off && off[0] == '1') return MMM_OK;  // static round-robin dealing (A/B timing)
+  if (!a->Broadcast) return MMM_OK;
+  ncclComm_t comm = (ncclComm_t)h->nccl_comm;
+  cudaIpcMemHandle_t handle;
+  memset(&handle, 0, sizeof(handle));
+  int* mine = nullptr;
+  int ok = 1;
+  if (h->dist_rank == 0) {
+    if (cudaMalloc((void**)&mine, 2 * sizeof(int)) != cudaSuccess || cudaMemset(mine, 0, 2 * sizeof(int)) != cudaSuccess ||
+        cudaIpcGetMemHandle(&handle, mine) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  // ship {ok, handle} from rank 0 to everybody
+  struct Msg { int ok; cudaIpcMemHandle_t handle; } msg;
+  msg.ok = ok;
+  msg.handle = handle;
+  Msg* d_msg = nullptr;
+  MMM_CUDA(h, cudaMalloc((void**)&d_msg, sizeof(Msg)));
+  MMM_CUDA(h, cudaMemcpyAsync(d_msg, &msg, sizeof(Msg), cudaMemcpyHostToDevice, h->stream));
+  ncclResult_t r = a->Broadcast(d_msg, d_msg, sizeof(Msg), ncclChar, 0, comm, h->stream);
+  if (r != ncclSuccess) { cudaFree(d_msg); return nccl_fail(h, a, r, "broadcast of the work-queue handle"); }
+  MMM_CUDA(h, cudaMemcpyAsync(&msg, d_msg, sizeof(Msg), cudaMemcpyDeviceToHost, h->stream));
+  MMM_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_msg);
+  // every rank reports whether it can reach the counters; the queue is used only if all can
+  int can = msg.ok;
+  int* ptr = mine;
+  if (can && h->dist_rank != 0) {
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, msg.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      can = 0;
+    }
+    ptr = (int*)p;
+  }
+  unsigned long long* d_votes = nullptr;
+  MMM_CUDA(h, cudaMalloc((void**)&d_votes, sizeof(unsigned long long)));
+  const unsigned long long vote = can ? 1ull : 0ull;
+  MMM_CUDA(h, cudaMemcpyAsync(d_votes, &vote, sizeof(vote), cudaMemcpyHostToDevice, h->stream));
+  r = a->AllReduce(d_votes, d_votes, 1, ncclUint64, ncclSum, comm, h->stream);
+  unsigned long long votes = 0;
+  if (r == ncclSuccess) {
+    cudaMemcpyAsync(&votes, d_votes, sizeof(votes), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d_votes);
+  if (r != ncclSuccess) return nccl_fail(h, a, r, "all-reduce of the work-queue votes");
+  if (votes == (unsigned long long)h->dist_world) {
+    h->d_gqueue = ptr;
+    h->gqueue_owner = h->dist_rank == 0;
+    h->gqueue_eval = 0;
+  } else {  // somebody cannot: everybody falls back to static dealing
+    if (h->dist_rank == 0) { if (mine) cudaFree(mine); }
+    else if (can && ptr) cudaIpcCloseMemHandle(ptr);
+  }
+  return MMM_OK;
+}
+
 void mmm_dist_destroy(mmm_system* h) {
+  if (h->d_gqueue) {
+    if (h->gqueue_owner) cudaFree(h->d_gqueue);
+    else cudaIpcCloseMemHandle(h->d_gqueue);
+    h->d_gqueue = nullptr;
+  }
   if (h->nccl_comm) {
     NcclApi* a = nccl();
     if (a->ok) a->CommDestroy((ncclComm_t)h->nccl_comm);
@@ -112,10 +189,14 @@ int mmm_dist_init(mmm_handle h, int rank, int world, const void* unique_id, int 
     if (r != ncclSuccess) return nccl_fail(h, a, r, "ncclCommInitRank");
     h->nccl_comm = comm;
     if (!h->ev_c0) { cudaEventCreate(&h->ev_c0); cudaEventCreate(&h->ev_c1); }
+    int rc = setup_global_queue(h, a);
+    if (rc) return rc;
   }
   h->scratch_sig = -2;  // re-size the scratch (local energy slots)
   return MMM_OK;
 }
+
+int mmm_dist_queue_mode(mmm_handle h) { return (h && h->d_gqueue) ? 1 : 0; }
 
 int mmm_dist_last_exchange_ms(mmm_handle h, float* ms_out) {
   if (!h || !ms_out) return MMM_ERR_ARG;

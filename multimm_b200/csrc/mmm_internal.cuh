@@ -166,6 +166,9 @@ struct mmm_system {
   int dist_rank = 0, dist_world = 1;
   bool dist_emulate = false;     // run every rank's share on this GPU, one after another (tests)
   void* nccl_comm = nullptr;
+  int* d_gqueue = nullptr;       // two ticket counters in rank 0's memory (CUDA IPC): one work queue for all GPUs
+  bool gqueue_owner = false;
+  int64_t gqueue_eval = 0;       // evaluations drawn from the queue so far (selects the counter)
   bool epair_aliased = false;    // dist: d_epair is the tail of the d_facc allocation (one all-reduce covers both)
   cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr;  // around the exchange step of the last evaluation (dist)
   int n3_items = 0;              // number of Newton-3 work items (their energy slots come first in d_epair)
@@ -213,7 +216,10 @@ struct mmm_system {
   int2* d_items_cut = nullptr;         // all-pairs item table the CUT kernel culls from
   int n_items_cut = 0;
   std::vector<int32_t> h_cut_iblk;     // i-block of every item of d_items_cut (slab boundaries of the sharded mode)
-  double* d_cut_npairs = nullptr;      // [n_items_cut] pairs inside the cut-off
+  double* d_cut_npairs = nullptr;      // [n_items_cut] pairs inside the cut-off (warp kernel: one per rank)
+  bool cut_warp = false;               // the one-warp-per-item kernel serves the cut-off pass (else the CTA-level CUT variant)
+  int n_cut_slots = 0;                 // energy slots of the cut-off pass
+  unsigned long long* d_cut_eacc = nullptr;  // [4] fixed-point energies + pair count (warp kernel)
   int sort_age = 0;                    // evaluations since the Morton order was rebuilt (0: rebuild now)
   // CHB on cluster centroids (mmm_chb_clusters.cu): coarse-stage surrogate, cut-off mode only
   bool chb_surrogate = false;    // requested (mmm_set_chb_surrogate)
@@ -266,7 +272,8 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only = false);
 // mmm_dist.cu
 int mmm_dist_allreduce(mmm_system* h);
 void mmm_dist_destroy(mmm_system* h);
-int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip);  // sorted arrays -> d_facc, d_epair (cut-off mode)
+int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip);
+int mmm_cut_warp_build_items(mmm_system* h, std::vector<int2>& items);  // sorted arrays -> d_facc, d_epair (cut-off mode)
 // mmm_cutoff.cu
 int mmm_launch_pair_cutoff_n3(mmm_system* h, const int* d_skip);
 int mmm_cutoff_read_grid(mmm_system* h, float* cell, int32_t* dim, float* origin);

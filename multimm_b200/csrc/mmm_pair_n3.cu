@@ -125,6 +125,7 @@ struct N3Args {
   int64_t npad;
   int n_items;
   int item_first, item_stride;  // this launch handles items item_first + k * item_stride
+  int sys_counter;              // the counter lives in another GPU's memory: system-scope atomics (NVLink)
   double fscale;             // U * 2^24
   double e_ev, e_gauss, e_chb;  // energy prefactors: eps sigma^p; -rc^2 U; dE
   // CUT variants (mmm_cutoff.cu): the arrays above are in Morton-sorted order
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
 
   for (;;) {
     __syncthreads();  // protects s_item, s_i, s_j, s_red across items
-    if (tid == 0) s_item = atomicAdd(A.counter, 1);
+    if (tid == 0) s_item = A.sys_counter ? atomicAdd_system(A.counter, 1) : atomicAdd(A.counter, 1);
     __syncthreads();
     const int item = A.item_first + s_item * A.item_stride;
     if (item >= A.n_items) break;
@@ -785,6 +786,224 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
   }
 }
 
+// ---- cut-off mode, one warp per work item -------------------------------------------------
+// In cut-off mode the surviving work is sparse: of the (512-bead i-block) x (256-bead stage) rectangles
+// the CTA-level kernel above visits, only a fraction of the (warp, tile) combinations lies within the
+// cut-off, and the other warps wait at the stage barriers.  Here every warp works alone: an item is
+// (64 consecutive sorted i-beads) x (a chunk of 32 stages); lane t tests stage t of the chunk against
+// the warp's i-box (one ballot), lanes 0-7 the tiles of a surviving stage (one ballot), and each
+// surviving 32-bead tile is staged in the warp's own slice of shared memory and evaluated by the same
+// step64 bodies (r^2 < rc^2 mask).  No block barrier anywhere.  j-side forces leave per tile, i-side
+// forces per item, both as 64-bit fixed point through the sort permutation; energies and the pair
+// count leave as 64-bit fixed point too (2^-20 kJ/mol), so that every sum is associative and the
+// result does not depend on which warp ran which item.
+constexpr double CW_EFIXED = 1048576.0;  // 2^20
+constexpr int CW_CHUNK = 32;             // stages per item
+
+struct CutWArgs {
+  const float4* pos4;
+  const float* soa;
+  const TileInfo* tiles;
+  const TileInfo* stage_boxes;
+  const int* perm;
+  unsigned long long* facc;
+  long long* eacc;   // [4] EV, COB, SCB energies and the pair count, fixed point
+  const int2* items; // (i-group, first stage of the chunk)
+  int* counter;
+  const int* skip;
+  int64_t npad;
+  int nstages, item_begin, item_end;
+  double fscale, e_ev, e_gauss;
+  N3Consts c;
+};
+
+template <int EVP, int GK>
+__global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_cut_warp(const CutWArgs A) {
+  __shared__ __align__(16) float4 s_j[N3_WARPS][MMM_TILE];
+  __shared__ __align__(16) float4 s_jxy[N3_WARPS][MMM_TILE];
+  __shared__ __align__(8) float2 s_jz[N3_WARPS][MMM_TILE];
+  __shared__ int s_it[N3_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane >> 2, b = lane & 3;
+  const N3Consts& c = A.c;
+  if (A.skip && *A.skip) return;
+
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = A.item_begin + atomicAdd(A.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= A.item_end) break;
+    const int2 it = A.items[item];
+    const int g = it.x, s0 = it.y, s1 = min(s0 + CW_CHUNK, A.nstages);
+    const int64_t ibase = (int64_t)g * 64;
+    IBeads I;
+    __syncwarp();  // the previous item's readers of s_it are done
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int64_t i0 = ibase + 8 * a + 2 * m;
+      I.x2[m] = *reinterpret_cast<const u64*>(A.soa + i0);
+      I.y2[m] = *reinterpret_cast<const u64*>(A.soa + A.npad + i0);
+      I.z2[m] = *reinterpret_cast<const u64*>(A.soa + 2 * A.npad + i0);
+      I.fx[2 * m] = I.fy[2 * m] = I.fz[2 * m] = 0.0f;
+      I.fx[2 * m + 1] = I.fy[2 * m + 1] = I.fz[2 * m + 1] = 0.0f;
+      if (m == b) {
+        s_it[warp][8 * a + 2 * m] = __float_as_int(A.pos4[i0].w);
+        s_it[warp][8 * a + 2 * m + 1] = __float_as_int(A.pos4[i0 + 1].w);
+      }
+    }
+    TileInfo ib = A.tiles[2 * g];
+    {
+      const TileInfo ib2 = A.tiles[2 * g + 1];
+      if (ib.cmin >= MMM_PAD_CHROM) {
+        ib = ib2;
+      } else if (ib2.cmin < MMM_PAD_CHROM) {
+        ib.lox = fminf(ib.lox, ib2.lox); ib.loy = fminf(ib.loy, ib2.loy); ib.loz = fminf(ib.loz, ib2.loz);
+        ib.hix = fmaxf(ib.hix, ib2.hix); ib.hiy = fmaxf(ib.hiy, ib2.hiy); ib.hiz = fmaxf(ib.hiz, ib2.hiz);
+      }
+    }
+    if (ib.cmin >= MMM_PAD_CHROM) continue;  // padding only
+    __syncwarp();
+
+    bool keep = false;
+    if (s0 + lane < s1) {
+      const TileInfo sb = A.stage_boxes[s0 + lane];
+      keep = sb.cmin < MMM_PAD_CHROM && box_dist2(ib, sb) < c.cut2;
+    }
+    unsigned smask = __ballot_sync(0xffffffffu, keep);
+    double de0 = 0.0, de1 = 0.0, de2 = 0.0, de3 = 0.0, poison = 0.0;
+
+    while (smask) {
+      const int s = s0 + __ffs(smask) - 1;
+      smask &= smask - 1u;
+      int cls = -1;
+      if (lane < N3_STEPS) {
+        const int t = s * N3_STEPS + lane;
+        if (t >= 2 * g) {  // tiles below the group's own belong to the groups before it
+          const TileInfo jt = A.tiles[t];
+          if (jt.cmin < MMM_PAD_CHROM) {
+            const float d2 = box_dist2(ib, jt);
+            if (d2 < c.cut2) cls = (GK != 0 && d2 < c.rg2) ? 4 : 0;
+          }
+        }
+      }
+      unsigned tmask = __ballot_sync(0xffffffffu, cls >= 0);
+      const unsigned nearmask = __ballot_sync(0xffffffffu, cls == 4);
+      while (tmask) {
+        const int q = __ffs(tmask) - 1;
+        tmask &= tmask - 1u;
+        const int t = s * N3_STEPS + q;
+        const float4 p = A.pos4[(int64_t)t * MMM_TILE + lane];
+        s_j[warp][lane] = p;
+        s_jxy[warp][lane] = make_float4(-p.x, -p.x, -p.y, -p.y);
+        s_jz[warp][lane] = make_float2(-p.z, -p.z);
+        __syncwarp();
+        const JDup sjd = {s_jxy[warp], s_jz[warp]};
+        EAcc E;
+        E.ev = E.scb = E.cob = E.chb = E.cnt = 0.0f;
+        E.ev2 = E.chb2 = E.cnt2 = E.scb2 = E.cob2 = pk2(0.0f, 0.0f);
+        float fj[3] = {0.0f, 0.0f, 0.0f};
+        double wgt = 1.0;
+        if (t < 2 * g + 2) {  // the group's own two tiles: ordered pairs, i side only, self masked, halved
+          const int self_d = (int)(ibase + 8 * a - (int64_t)t * MMM_TILE);
+          step64<EVP, GK, 0, true, false, true>(s_j[warp], sjd, a, b, I, fj, E, c, s_it[warp] + 8 * a, self_d);
+          wgt = 0.5;
+        } else {
+          if (GK != 0 && ((nearmask >> q) & 1u))
+            step64<EVP, GK, 0, false, true, true>(s_j[warp], sjd, a, b, I, fj, E, c, s_it[warp] + 8 * a, 0);
+          else
+            step64<EVP, 0, 0, false, true, true>(s_j[warp], sjd, a, b, I, fj, E, c, s_it[warp] + 8 * a, 0);
+          if (fj[0] != 0.0f || fj[1] != 0.0f || fj[2] != 0.0f) {  // lane l holds j-bead l of the tile
+            const int64_t j = A.perm[(int64_t)t * MMM_TILE + lane];
+            red_fixed(A.facc + j, -fj[0], A.fscale, poison);
+            red_fixed(A.facc + A.npad + j, -fj[1], A.fscale, poison);
+            red_fixed(A.facc + 2 * A.npad + j, -fj[2], A.fscale, poison);
+          }
+        }
+        {
+          float lo, hi;
+          unpk2(E.ev2, lo, hi); E.ev += lo + hi;
+          if (GK & 1) { unpk2(E.scb2, lo, hi); E.scb += lo + hi; }
+          if (GK & 2) { unpk2(E.cob2, lo, hi); E.cob += lo + hi; }
+          unpk2(E.cnt2, lo, hi); E.cnt += lo + hi;
+        }
+        de0 += wgt * (double)E.ev;
+        de1 += wgt * (double)E.cob;
+        de2 += wgt * (double)E.scb;
+        de3 += wgt * (double)E.cnt;
+        __syncwarp();  // everybody has read the tile before the next one overwrites it
+      }
+    }
+
+    // i-side emission: butterfly over the 4 b-lanes, then lane b emits beads 2b and 2b + 1
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      I.fx[ii] += __shfl_xor_sync(0xffffffffu, I.fx[ii], 1);
+      I.fy[ii] += __shfl_xor_sync(0xffffffffu, I.fy[ii], 1);
+      I.fz[ii] += __shfl_xor_sync(0xffffffffu, I.fz[ii], 1);
+      I.fx[ii] += __shfl_xor_sync(0xffffffffu, I.fx[ii], 2);
+      I.fy[ii] += __shfl_xor_sync(0xffffffffu, I.fy[ii], 2);
+      I.fz[ii] += __shfl_xor_sync(0xffffffffu, I.fz[ii], 2);
+    }
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      if ((ii >> 1) == b && (I.fx[ii] != 0.0f || I.fy[ii] != 0.0f || I.fz[ii] != 0.0f)) {
+        const int64_t i = A.perm[ibase + 8 * a + ii];
+        red_fixed(A.facc + i, I.fx[ii], A.fscale, poison);
+        red_fixed(A.facc + A.npad + i, I.fy[ii], A.fscale, poison);
+        red_fixed(A.facc + 2 * A.npad + i, I.fz[ii], A.fscale, poison);
+      }
+    }
+    // energies and pair count of the item: fixed point, so that the total is the same in any order
+    de0 = warp_sum_d(de0 * A.e_ev + poison);
+    de1 = warp_sum_d(de1 * A.e_gauss);
+    de2 = warp_sum_d(de2 * A.e_gauss);
+    de3 = warp_sum_d(de3);
+    if (lane < 4) {
+      const double v = lane == 0 ? de0 : (lane == 1 ? de1 : (lane == 2 ? de2 : de3));
+      // a NaN / Inf force poisons the EV energy: keep it visible (the largest magnitude) instead of wrapping
+      const long long fx = isfinite(v) ? __double2ll_rn(v * CW_EFIXED) : 0x7fffffffffffffffLL;
+      if (fx != 0) atomicAdd(reinterpret_cast<unsigned long long*>(A.eacc + lane), (unsigned long long)fx);
+    }
+  }
+}
+
+// fixed-point totals -> the energy slot of this rank's cut-off pass, and the pair count; re-arm
+__global__ void k_cut_finish(long long* __restrict__ eacc, double* __restrict__ epair_slot, double* __restrict__ npairs,
+                             const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  const int t = threadIdx.x;
+  if (t < 4) {
+    const long long v = eacc[t];
+    eacc[t] = 0;
+    const double d = v == 0x7fffffffffffffffLL ? __longlong_as_double(0x7ff8000000000000LL) : (double)v / CW_EFIXED;
+    if (t < 3) epair_slot[t] = d;
+    else { npairs[0] = d; epair_slot[3] = 0.0; }
+  }
+}
+
+template <int EVP, int GK>
+int launch_cut_warp(mmm_system* h, const CutWArgs& A) {
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pair_cut_warp<EVP, GK>, N3_THREADS, 0);
+  if (occ < 1) occ = 1;
+  int grid = h->sm_count * occ;
+  const int n_local = A.item_end - A.item_begin;
+  if (grid * N3_WARPS > n_local) grid = (n_local + N3_WARPS - 1) / N3_WARPS;
+  if (grid < 1) grid = 1;
+  k_pair_cut_warp<EVP, GK><<<grid, N3_THREADS, 0, h->stream>>>(A);
+  return 0;
+}
+
+template <int EVP>
+int launch_cut_warp_gk(mmm_system* h, const CutWArgs& A, int gk) {
+  switch (gk) {
+    case 0: return launch_cut_warp<EVP, 0>(h, A);
+    case 1: return launch_cut_warp<EVP, 1>(h, A);
+    case 2: return launch_cut_warp<EVP, 2>(h, A);
+    default: return launch_cut_warp<EVP, 3>(h, A);
+  }
+}
+
 template <int EVP, int GK, bool CHB, bool CUT>
 int launch_n3(mmm_system* h, const N3Args& A) {
   int occ = 1;
@@ -921,6 +1140,7 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   A.stage_boxes = nullptr;
   A.perm = nullptr;
   A.npairs = nullptr;
+  A.sys_counter = 0;
   fill_consts(p, chb_only, true, A);
   const N3Consts& c = A.c;
 
@@ -936,7 +1156,20 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   for (int r = r0; r < r1; ++r) {
     A.item_first = r;
     A.item_stride = h->dist_world;
-    MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
+    if (h->d_gqueue && !h->dist_emulate && !chb_only) {
+      // (exact mode only: there the all-reduce of every evaluation separates the two counters' uses)
+      // one queue for all GPUs: every rank draws from counter (k & 1) of evaluation k; rank 0 re-arms
+      // the other counter, which nobody touches until the all-reduce of this evaluation has passed
+      const int which = (int)(h->gqueue_eval & 1);
+      if (h->gqueue_owner) MMM_CUDA(h, cudaMemsetAsync(h->d_gqueue + (which ^ 1), 0, sizeof(int), h->stream));
+      A.counter = h->d_gqueue + which;
+      A.sys_counter = 1;
+      A.item_first = 0;
+      A.item_stride = 1;
+      h->gqueue_eval++;
+    } else {
+      MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
+    }
     if (chb_only) launch_n3<0, 0, true, false>(h, A);
     else if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
     else launch_n3_evp<3>(h, A, c.gk, chb);
@@ -947,9 +1180,63 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   return MMM_OK;
 }
 
+// Items of the one-warp-per-item cut-off kernel: (group of 64 sorted beads, chunk of 32 stages from the
+// group's own stage on), groups in ascending order (the sharded mode cuts this list into slabs).
+int mmm_cut_warp_build_items(mmm_system* h, std::vector<int2>& items) {
+  const int ngroups = (int)((h->n + 63) / 64), nstages = (int)(h->npad / N3_JB);
+  items.clear();
+  for (int g = 0; g < ngroups; ++g)
+    for (int s = g / 4; s < nstages; s += CW_CHUNK) items.push_back(make_int2(g, s));
+  return MMM_OK;
+}
+
+int mmm_launch_pair_cut_warp(mmm_system* h, const int* d_skip) {
+  const PairParams& p = h->pp;
+  N3Args tmp;
+  fill_consts(p, false, false, tmp);
+  CutWArgs A;
+  A.pos4 = h->d_pos4_sorted;
+  A.soa = h->d_soa_sorted;
+  A.tiles = h->d_tiles_sorted;
+  A.stage_boxes = h->d_stage_boxes;
+  A.perm = h->d_order;
+  A.facc = h->d_facc;
+  A.eacc = reinterpret_cast<long long*>(h->d_cut_eacc);
+  A.items = h->d_items_cut;
+  A.counter = h->d_counter + 1;
+  A.skip = d_skip;
+  A.npad = h->npad;
+  A.nstages = (int)(h->npad / N3_JB);
+  A.fscale = tmp.fscale;
+  A.e_ev = tmp.e_ev;
+  A.e_gauss = tmp.e_gauss;
+  A.c = tmp.c;
+  // Several GPUs: contiguous slabs of 64-bead groups of the Morton order, one slab per rank
+  const int ngroups = (int)((h->n + 63) / 64);
+  const int r0 = h->dist_emulate ? 0 : h->dist_rank, r1 = h->dist_emulate ? h->dist_world : h->dist_rank + 1;
+  for (int r = r0; r < r1; ++r) {
+    const int g0 = (int)((int64_t)ngroups * r / h->dist_world), g1 = (int)((int64_t)ngroups * (r + 1) / h->dist_world);
+    const auto& ig = h->h_cut_iblk;  // group of every item
+    A.item_begin = (int)(std::lower_bound(ig.begin(), ig.end(), g0) - ig.begin());
+    A.item_end = (int)(std::lower_bound(ig.begin(), ig.end(), g1) - ig.begin());
+    MMM_CUDA(h, cudaMemsetAsync(h->d_counter + 1, 0, sizeof(int), h->stream));
+    if (A.item_end > A.item_begin) {
+      if (p.ev_power == 6.0f) launch_cut_warp_gk<6>(h, A, A.c.gk);
+      else launch_cut_warp_gk<3>(h, A, A.c.gk);
+      h->launches++;
+    }
+    // this rank's slot (one writer per slot: the sharded sum stays exact)
+    k_cut_finish<<<1, 32, 0, h->stream>>>(A.eacc, h->d_epair + 4 * ((size_t)h->cells_item0 + r), h->d_cut_npairs + r, d_skip);
+    h->launches++;
+  }
+  MMM_CUDA(h, cudaGetLastError());
+  return MMM_OK;
+}
+
 // Cut-off mode (mmm_cutoff.cu): EV / COB / SCB truncated at rc over the Morton-sorted arrays; the
 // item table is the all-pairs one, the kernel culls.  Energy slots follow those of the CHB-only pass.
 int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip) {
+  if (h->cut_warp) return mmm_launch_pair_cut_warp(h, d_skip);
   const PairParams& p = h->pp;
   N3Args A;
   A.pos4 = h->d_pos4_sorted;
@@ -967,6 +1254,7 @@ int mmm_launch_pair_n3_cut(mmm_system* h, const int* d_skip) {
   A.stage_boxes = h->d_stage_boxes;
   A.perm = h->d_order;
   A.npairs = h->d_cut_npairs;
+  A.sys_counter = 0;
   fill_consts(p, false, false, A);
   // Several GPUs: the sorted order is cut into contiguous slabs of i-blocks — spatial slabs along
   // the Morton curve — and rank r evaluates the items of its slab (pairs with the stages at or above

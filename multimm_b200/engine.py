@@ -219,6 +219,11 @@ class Engine:
         self._ck(self._lib.mmm_dist_emulate(self._h, int(world)))
 
     @property
+    def dist_queue_mode(self) -> int:
+        """1: all ranks draw work items from one queue over NVLink peer memory; 0: static round-robin dealing."""
+        return int(self._lib.mmm_dist_queue_mode(self._h))
+
+    @property
     def last_collective_ms(self) -> float:
         """ms of the exchange step of the most recent evaluation on this rank (0 without a communicator)."""
         ms = C.c_float()

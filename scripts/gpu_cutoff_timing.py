@@ -17,7 +17,7 @@ with tempfile.TemporaryDirectory() as tmp:
     eng = m.engine
     x0 = m.positions.copy()
     eng.set_cutoff(rc)
-    for name, pref in (("n3_sorted_tiles", 0), ("cells_gather", 1)):
+    for name, pref in (("n3_warp_per_item", 0), ("n3_cta_level", 2), ("cells_gather", 1)):
         eng.set_pair_kernel(pref)
         eng.set_positions(x0)
         e, _ = eng.energy_forces()
@@ -31,7 +31,7 @@ with tempfile.TemporaryDirectory() as tmp:
     eng.set_positions(x0)
     eng.minimize(tol=10.0, max_iter=200)
     x1 = eng.get_positions()
-    for name, pref in (("n3_sorted_tiles_relaxed", 0), ("cells_gather_relaxed", 1)):
+    for name, pref in (("n3_warp_per_item_relaxed", 0), ("n3_cta_level_relaxed", 2), ("cells_gather_relaxed", 1)):
         eng.set_pair_kernel(pref)
         eng.set_positions(x1)
         eng.evaluate_timed(5, flush_l2=False)
@@ -43,9 +43,9 @@ with tempfile.TemporaryDirectory() as tmp:
     eng.set_positions(x1)
     eng.evaluate_timed(5, flush_l2=False)
     tot, pair = eng.evaluate_timed(40, flush_l2=False)
-    out["n3_sorted_tiles_relaxed_chb_clusters"] = dict(ms_per_eval=tot / 40, cut_pass_ms=pair / 40)
+    out["n3_warp_per_item_relaxed_chb_clusters"] = dict(ms_per_eval=tot / 40, cut_pass_ms=pair / 40)
     # two-stage minimisation (MIN_COARSE_CUTOFF): coarse stage on the truncated potential, exact stage after
-    for name, surrogate in (("two_stage_chb_clusters", True), ("two_stage_chb_exact", False)):
+    for name, surrogate in (("two_stage_chb_exact", False),):
         eng.set_cutoff(rc)
         eng.set_chb_surrogate(surrogate)
         eng.set_positions(x0)

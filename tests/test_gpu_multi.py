@@ -27,6 +27,7 @@ def _rank(rank, world, port, q, cutoff=0.0):
     e, f = eng.energy_forces()
     rep = eng.minimize(tol=10.0, max_iter=20)
     rep["exchange_ms"] = eng.last_collective_ms
+    rep["queue_mode"] = eng.dist_queue_mode
     x = eng.get_positions()
     eng.close()
     dist.barrier()
@@ -66,6 +67,10 @@ def test_two_gpus_one_system(built_lib, cutoff):
         assert rep["e_final"] == rep0["e_final"] and rep["evaluations"] == rep0["evaluations"]
         assert np.array_equal(x, x0)
         assert rep["exchange_ms"] > 0.0  # the exchange step ran and was timed
+        # exact mode draws its items from one queue over NVLink peer memory when CUDA IPC works (else static
+        # dealing); either way the bits above are the single-GPU bits
+        assert rep["queue_mode"] in (0, 1)
+        print(f"rank {rank}: cutoff {cutoff}, work queue mode {rep['queue_mode']}, exchange {rep['exchange_ms']:.3f} ms")
 
 
 def test_ensemble_is_dealt_to_two_gpus(built_lib, tmp_path):

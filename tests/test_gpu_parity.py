@@ -172,11 +172,15 @@ def test_cutoff_mode_two_kernels_agree(built_lib):
     eng.set_pair_kernel(1)
     e2, f2 = eng.energy_forces()
     p2 = eng.cell_grid()["pairs"]
+    eng.set_pair_kernel(2)  # the CTA-level variant of the Newton-3 cut-off pass (default: one warp per item)
+    e3, f3 = eng.energy_forces()
+    p3 = eng.cell_grid()["pairs"]
     eng.close()
     sysd = to_oracle(case, cutoff=rc)
     e_ref, f_ref = O.energy_forces(sysd, case["x"])
-    assert p1 == p2 == O.count_pairs(sysd, case["x"])
-    for e in (e1, e2):
+    assert p1 == p2 == p3 == O.count_pairs(sysd, case["x"])
+    assert np.array_equal(f1, f3)  # same pairs, same FP32 pair arithmetic, integer accumulation: same bits
+    for e in (e1, e2, e3):
         for t in range(10):
             assert abs(e[t] - e_ref[t]) <= E_TOL * max(abs(e_ref[t]), 1e-12) + 1e-9, (O.TERM_NAMES[t], e[t], e_ref[t])
     assert force_rel_err(f1, f_ref) <= F_TOL and force_rel_err(f2, f_ref) <= F_TOL and force_rel_err(f1, f2) <= F_TOL
