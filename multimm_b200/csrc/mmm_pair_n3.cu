@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
 // count leave as 64-bit fixed point too (2^-20 kJ/mol), so that every sum is associative and the
 // result does not depend on which warp ran which item.
 constexpr double CW_EFIXED = 1048576.0;  // 2^20
-constexpr int CW_CHUNK = 32;             // stages per item
+constexpr int CW_CHUNK = 8;              // stages per item: fine enough that the items near the diagonal (where the work is) spread over all warps
 
 struct CutWArgs {
   const float4* pos4;
