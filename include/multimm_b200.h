@@ -242,12 +242,6 @@ int mmm_set_pair_kernel(mmm_handle h, int which);
  * exact pass a truncated evaluation otherwise carries).  A proper potential with an exact gradient;
  * used by the opt-in two-stage minimisation (MIN_COARSE_CUTOFF), whose exact stage follows. */
 int mmm_set_chb_surrogate(mmm_handle h, int on);
-/* Warm start: with on != 0, an mmm_minimize that follows another one on the same handle WITHOUT new
- * positions in between takes its first direction from the L-BFGS history the previous run left
- * (instead of steepest descent), and replaces that history pair by pair.  For the exact stage of the
- * two-stage minimisation, whose potential differs from the coarse stage's only by the truncated tail.
- * Default off: a plain mmm_minimize is liblbfgs from a cold start, as OpenMM runs it. */
-int mmm_set_warm_start(mmm_handle h, int on);
 /* mmm_minimize replays one captured CUDA graph per evaluation (per Morton-order period in cut-off
  * mode) instead of 6-7 separate launches; on = 0 goes back to plain launches (A/B timing, debugging).
  * Results are identical either way. */

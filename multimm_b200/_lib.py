@@ -32,7 +32,7 @@ EXPORTS = (
     "mmm_set_positions", "mmm_get_positions", "mmm_set_positions_device", "mmm_get_positions_device",
     "mmm_hilbert_init", "mmm_hilbert_points",
     "mmm_energy_forces", "mmm_energy_forces_device", "mmm_evaluate_n", "mmm_evaluate_timed", "mmm_minimize",
-    "mmm_launch_count", "mmm_set_graph", "mmm_set_chb_surrogate", "mmm_set_warm_start", "mmm_set_pair_kernel", "mmm_pair_kernel_in_use", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_get_cell_grid", "mmm_measure_fp32_peak",
+    "mmm_launch_count", "mmm_set_graph", "mmm_set_chb_surrogate", "mmm_set_pair_kernel", "mmm_pair_kernel_in_use", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_get_cell_grid", "mmm_measure_fp32_peak",
     "mmm_dist_unique_id", "mmm_dist_init", "mmm_dist_emulate", "mmm_dist_last_exchange_ms", "mmm_dist_queue_mode",
     "mmm_mean_pair_distance", "mmm_contact_map", "mmm_md_configure", "mmm_set_velocities_to_temperature", "mmm_set_velocities", "mmm_get_velocities", "mmm_md_run",
 )
@@ -103,7 +103,6 @@ def load():
         "mmm_set_pair_kernel": (i32, [vp, i32]),
         "mmm_set_graph": (i32, [vp, i32]),
         "mmm_set_chb_surrogate": (i32, [vp, i32]),
-        "mmm_set_warm_start": (i32, [vp, i32]),
         "mmm_pair_kernel_in_use": (i32, [vp]),
         "mmm_last_pair_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "mmm_get_cell_list": (i32, [vp, vp, vp]),

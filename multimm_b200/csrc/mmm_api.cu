@@ -331,7 +331,6 @@ int mmm_set_positions(mmm_handle h, const double* xyz) {
   if (rc) return rc;
   h->positions_set = true;
   h->sort_age = 0;  // cut-off mode: new positions from outside, rebuild the Morton order
-  h->lbfgs_valid = false;
   return MMM_OK;
 }
 
@@ -361,7 +360,6 @@ int mmm_set_positions_device(mmm_handle h, const double* d_xyz) {
   if (rc) return rc;
   h->positions_set = true;
   h->sort_age = 0;
-  h->lbfgs_valid = false;
   return MMM_OK;
 }
 
@@ -385,7 +383,6 @@ int mmm_hilbert_init(mmm_handle h, int p, double spacing_nm) {
   if ((rc = refresh_center_from_device(h))) return rc;
   h->positions_set = true;
   h->sort_age = 0;
-  h->lbfgs_valid = false;
   return MMM_OK;
 }
 
@@ -707,12 +704,6 @@ int mmm_pair_kernel_in_use(mmm_handle h) { return h ? h->pair_mode : 0; }
 int mmm_set_chb_surrogate(mmm_handle h, int on) {
   if (!h) return MMM_ERR_ARG;
   h->chb_surrogate = on != 0;
-  return MMM_OK;
-}
-
-int mmm_set_warm_start(mmm_handle h, int on) {
-  if (!h) return MMM_ERR_ARG;
-  h->warm_start = on != 0;
   return MMM_OK;
 }
 

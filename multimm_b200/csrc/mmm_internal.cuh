@@ -83,7 +83,6 @@ struct LbfgsState {
   int end;         // next slot to write
   int bound;       // number of valid history pairs
   int ls_count;
-  int warm;        // the first direction comes from the history a previous minimisation left (mmm_set_warm_start)
   long long k;     // liblbfgs iteration counter (starts at 1)
   long long iterations, evaluations, max_iter;
   // scalars
@@ -95,7 +94,7 @@ struct LbfgsState {
   double e_terms[MMM_NUM_TERMS];  // per-term energies of the most recent evaluation
 };
 
-enum ApplyFlag { APPLY_NONE = 0, APPLY_INIT = 1, APPLY_RETRY = 2, APPLY_ACCEPT = 3, APPLY_RESTORE = 4, APPLY_WARM = 5 };
+enum ApplyFlag { APPLY_NONE = 0, APPLY_INIT = 1, APPLY_RETRY = 2, APPLY_ACCEPT = 3, APPLY_RESTORE = 4 };
 
 // ---------------------------------------------------------------------------------------
 // the handle
@@ -188,8 +187,6 @@ struct mmm_system {
   double *d_xp = nullptr, *d_gp = nullptr, *d_d = nullptr;
   double *d_S = nullptr, *d_Y = nullptr;  // [m][3n]
   int* h_done = nullptr;         // pinned mirror of LbfgsState::done / counters
-  bool warm_start = false;       // mmm_set_warm_start: the next mmm_minimize starts from the previous run's history
-  bool lbfgs_valid = false;      // d_S / d_Y / d_lb hold the history of a minimisation that ended at the current positions
 
   // MD relaxation (mmm_md.cu)
   double* d_v = nullptr;         // [3n] velocities, nm/ps

@@ -148,36 +148,6 @@ __device__ void decide(const DecideArgs& A) {
   }
 }
 
-// Two-loop recursion on coefficients over {s_l}, {y_l}, g: d = cg g + sum_l (cs_l s_l + cy_l y_l).
-// Returns d . g.
-__device__ double two_loop(const LbfgsState* st, double (*Gss)[M], double (*Gsy)[M], double (*Gyy)[M], const double* gs,
-                           const double* gy, double gg, int end, int bound, double scale, double* cs, double* cy,
-                           double& cg) {
-  double alpha[M];
-  cg = -1.0;
-  for (int l = 0; l < M; ++l) { cs[l] = 0.0; cy[l] = 0.0; alpha[l] = 0.0; }
-  int j = end;
-  for (int q = 0; q < bound; ++q) {
-    j = (j + M - 1) % M;
-    double sd = cg * gs[j];
-    for (int l = 0; l < bound; ++l) sd += cs[l] * Gss[j][l] + cy[l] * Gsy[j][l];
-    alpha[j] = sd / st->ys[j];
-    cy[j] -= alpha[j];
-  }
-  cg *= scale;
-  for (int l = 0; l < M; ++l) { cs[l] *= scale; cy[l] *= scale; }
-  for (int q = 0; q < bound; ++q) {
-    double yd = cg * gy[j];
-    for (int l = 0; l < bound; ++l) yd += cs[l] * Gsy[l][j] + cy[l] * Gyy[j][l];
-    const double beta = yd / st->ys[j];
-    cs[j] += alpha[j] - beta;
-    j = (j + 1) % M;
-  }
-  double dg = cg * gg;
-  for (int l = 0; l < bound; ++l) dg += cs[l] * gs[l] + cy[l] * gy[l];
-  return dg;
-}
-
 __device__ void decide_serial(LbfgsState* st, const double* s_val, double* eterms, double (*G)[M][M]) {
   double (*Gss)[M] = G[0];
   double (*Gsy)[M] = G[1];
@@ -204,30 +174,6 @@ __device__ void decide_serial(LbfgsState* st, const double* s_val, double* eterm
     st->xnorm = xnorm;
     if (!finite) { st->done = 4; st->flag = APPLY_NONE; return; }
     if (gnorm / xnorm <= st->epsilon) { st->done = 1; st->flag = APPLY_NONE; return; }
-    if (st->warm && st->bound > 0) {
-      // Warm start (mmm_set_warm_start): the history of the previous minimisation — of a potential close to
-      // this one, e.g. the truncated potential of the coarse stage — gives the first direction instead of
-      // steepest descent; its pairs are replaced by this potential's as the iterations go.
-      double gs[M], gy[M], cs[M], cy[M], cg;
-      for (int l = 0; l < M; ++l) { gs[l] = D[D_GS + l]; gy[l] = D[D_GY + l]; }
-      const int last = (st->end + M - 1) % M;
-      const double dg0 = two_loop(st, Gss, Gsy, Gyy, gs, gy, D[D_GG], st->end, st->bound, st->ys[last] / Gyy[last][last],
-                                  cs, cy, cg);
-      if (dg0 < 0.0 && isfinite(dg0)) {
-        for (int l = 0; l < M; ++l) { st->delta[l] = cs[l]; st->delta[M + l] = cy[l]; }
-        st->delta[2 * M] = cg;
-        st->finit = f;
-        st->dginit = dg0;
-        st->step = 1.0;
-        st->ls_count = 0;
-        st->phase = 2;
-        st->flag = APPLY_WARM;
-        return;
-      }
-      st->bound = 0;  // not a descent direction for this potential: forget the history
-      st->end = 0;
-      st->k = 1;
-    }
     st->step = 1.0 / gnorm;  // d = -g
     st->finit = f;
     st->dginit = -D[D_GG];
@@ -271,7 +217,7 @@ __device__ void decide_serial(LbfgsState* st, const double* s_val, double* eterm
   st->gnorm = gnorm;
   st->xnorm = xnorm;
   if (gnorm / xnorm <= st->epsilon) { st->done = 1; st->flag = APPLY_NONE; return; }
-  if (st->max_iter != 0 && st->iterations >= st->max_iter) { st->done = 2; st->flag = APPLY_NONE; return; }
+  if (st->max_iter != 0 && st->max_iter < st->k + 1) { st->done = 2; st->flag = APPLY_NONE; return; }
 
   // history update: s_e = step * d, y_e = g - gp go to slot e
   const int e = st->end, bound_old = st->bound;
@@ -300,8 +246,29 @@ __device__ void decide_serial(LbfgsState* st, const double* s_val, double* eterm
   st->end = end;
   st->bound = bound;
 
-  double cs[M], cy[M], cg;
-  const double dginit = two_loop(st, Gss, Gsy, Gyy, gs, gy, gg, end, bound, ys / yy, cs, cy, cg);
+  // two-loop recursion on coefficients over {s_l}, {y_l}, g
+  double cs[M], cy[M], alpha[M], cg = -1.0;
+  for (int l = 0; l < M; ++l) { cs[l] = 0.0; cy[l] = 0.0; alpha[l] = 0.0; }
+  int j = end;
+  for (int q = 0; q < bound; ++q) {
+    j = (j + M - 1) % M;
+    double sd = cg * gs[j];
+    for (int l = 0; l < bound; ++l) sd += cs[l] * Gss[j][l] + cy[l] * Gsy[j][l];
+    alpha[j] = sd / st->ys[j];
+    cy[j] -= alpha[j];
+  }
+  const double scale = ys / yy;
+  cg *= scale;
+  for (int l = 0; l < M; ++l) { cs[l] *= scale; cy[l] *= scale; }
+  for (int q = 0; q < bound; ++q) {
+    double yd = cg * gy[j];
+    for (int l = 0; l < bound; ++l) yd += cs[l] * Gsy[l][j] + cy[l] * Gyy[j][l];
+    const double beta = yd / st->ys[j];
+    cs[j] += alpha[j] - beta;
+    j = (j + 1) % M;
+  }
+  double dginit = cg * gg;
+  for (int l = 0; l < bound; ++l) dginit += cs[l] * gs[l] + cy[l] * gy[l];
   for (int l = 0; l < M; ++l) { st->delta[l] = cs[l]; st->delta[M + l] = cy[l]; }
   st->delta[2 * M] = cg;
   st->slot = e;
@@ -358,16 +325,6 @@ __global__ void __launch_bounds__(256) k_apply(const LbfgsState* __restrict__ st
       }
       d[e] = dn;
       x[e] = xe + step * dn;
-    } else if (flag == APPLY_WARM) {
-      const double xe = x[e], ge = g[e];
-      xp[e] = xe;
-      gp[e] = ge;
-      double dn = cg * ge;
-#pragma unroll
-      for (int l = 0; l < M; ++l)
-        if (l < bound) dn += cs[l] * S[(size_t)l * n3 + e] + cy[l] * Y[(size_t)l * n3 + e];
-      d[e] = dn;
-      x[e] = xe + step * dn;
     } else {  // APPLY_RESTORE
       x[e] = xp[e];
       g[e] = gp[e];
@@ -419,22 +376,8 @@ int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report
   // (one host read of |x|^2 before the loop starts; nothing is read back per iteration)
   LbfgsState init;
   memset(&init, 0, sizeof(init));
-  const bool warm = h->warm_start && h->lbfgs_valid;
-  if (warm) {  // keep the history (slots, Gram matrices, y.s) the previous run left; reset the controller
-    MMM_CUDA(h, cudaMemcpyAsync(&init, h->d_lb, sizeof(init), cudaMemcpyDeviceToHost, h->stream));
-    MMM_CUDA(h, cudaStreamSynchronize(h->stream));
-    init.flag = APPLY_NONE;
-    init.done = 0;
-    init.ls_status = 0;
-    init.ls_count = 0;
-    init.iterations = init.evaluations = 0;
-    init.warm = 1;
-    if (init.k < 1) init.k = 1;
-  } else {
-    init.k = 1;
-  }
-  h->lbfgs_valid = false;
   init.phase = 1;
+  init.k = 1;
   init.max_iter = max_iter;
   init.epsilon = -1.0;  // filled below
   {
@@ -527,7 +470,6 @@ int mmm_run_minimize(mmm_system* h, double tol, int64_t max_iter, mmm_min_report
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
   h->sort_age = 0;  // whatever comes next re-sorts
-  h->lbfgs_valid = true;  // S, Y and the Gram matrices describe the neighbourhood of the end point
   // a failed line search leaves a pending RESTORE (x <- xp)
   k_apply<<<grid_apply, 256, 0, h->stream>>>(h->d_lb, n3, h->d_x, h->d_g, h->d_xp, h->d_gp, h->d_d, h->d_S, h->d_Y);
   k_clear_flag<<<1, 1, 0, h->stream>>>(h->d_lb);

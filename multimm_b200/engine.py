@@ -244,10 +244,6 @@ class Engine:
         (coarse stage of the two-stage minimisation; not the reference's potential)."""
         self._ck(self._lib.mmm_set_chb_surrogate(self._h, int(bool(on))))
 
-    def set_warm_start(self, on: bool):
-        """The next minimize() that follows another one without new positions starts from its L-BFGS history."""
-        self._ck(self._lib.mmm_set_warm_start(self._h, int(bool(on))))
-
     def set_graph(self, on: bool):
         """minimize(): replay a captured CUDA graph per evaluation (default) or launch kernel by kernel."""
         self._ck(self._lib.mmm_set_graph(self._h, int(bool(on))))

@@ -293,13 +293,9 @@ class MultiMM:
             self.coarse_report = self.engine.minimize(tol=tol, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
             self.engine.set_cutoff(0.0)
             self.engine.set_chb_surrogate(False)
-            # the exact stage starts from the coarse stage's L-BFGS history (the potentials differ by the
-            # truncated tail only), not from steepest descent
-            self.engine.set_warm_start(True)
             self.timings["coarse_iterations"] = int(self.coarse_report["iterations"])
             self.timings["coarse_seconds"] = float(self.coarse_report["wall_seconds"])
         self.report = self.engine.minimize(tol=tol, max_iter=max_iter)
-        self.engine.set_warm_start(False)
         self.positions = self.engine.get_positions()
         self.timings["minimize_s"] = time.time() - t0
         t1 = time.time()

@@ -45,8 +45,7 @@ with tempfile.TemporaryDirectory() as tmp:
     tot, pair = eng.evaluate_timed(40, flush_l2=False)
     out["n3_warp_per_item_relaxed_chb_clusters"] = dict(ms_per_eval=tot / 40, cut_pass_ms=pair / 40)
     # two-stage minimisation (MIN_COARSE_CUTOFF): coarse stage on the truncated potential, exact stage after
-    for name, surrogate, warm in (("two_stage_cold", False, False), ("two_stage_warm", False, True),
-                                  ("two_stage_chb_clusters_warm", True, True)):
+    for name, surrogate in (("two_stage_chb_exact", False),):
         eng.set_cutoff(rc)
         eng.set_chb_surrogate(surrogate)
         eng.set_positions(x0)
@@ -54,9 +53,7 @@ with tempfile.TemporaryDirectory() as tmp:
         rep_c = eng.minimize(tol=10.0, max_iter=20000)
         eng.set_cutoff(0.0)
         eng.set_chb_surrogate(False)
-        eng.set_warm_start(warm)
         rep_e = eng.minimize(tol=10.0, max_iter=0)
-        eng.set_warm_start(False)
         out[name] = dict(total_s=time.perf_counter() - t0, coarse=rep_c, exact=rep_e)
         print(json.dumps({name: out[name]}), flush=True)
     m.close()

@@ -444,33 +444,3 @@ def _chb_only_forces(case):
     only["ev"] = None
     _, f = O.energy_forces(to_oracle(only), case["x"])
     return f
-
-
-def test_warm_start_of_the_exact_stage(built_lib):
-    """Two-stage minimisation: the exact stage takes its first direction from the coarse stage's L-BFGS
-    history (mmm_set_warm_start).  Same stopping rule met on the exact potential, the oracle agrees with
-    the reported energy, and a cold second stage never needs fewer iterations by much; new positions
-    from outside invalidate the history (cold start again, same result as a fresh engine)."""
-    case = make_case(8000, n_chrom=3, seed=19, noise=0.0)
-    out = {}
-    for warm in (False, True):
-        eng = to_engine(case, cutoff=0.5)
-        rep_c = eng.minimize(tol=10.0, max_iter=20000)
-        eng.set_cutoff(0.0)
-        eng.set_warm_start(warm)
-        rep_e = eng.minimize(tol=10.0, max_iter=0)
-        assert rep_e["converged"] == 1 and rep_e["rms_force"] <= 10.0 * 1.0001, rep_e
-        e_chk = O.energy_forces(to_oracle(case), eng.get_positions(), want_forces=False)[0].sum()
-        assert abs(e_chk - rep_e["e_final"]) <= 1e-5 * abs(e_chk)
-        out[warm] = (rep_c, rep_e)
-        if warm:  # set_positions drops the history: identical to a cold engine from here
-            eng.set_positions(case["x"])
-            rep_cold = eng.minimize(tol=10.0, max_iter=15)
-            eng2 = to_engine(case)
-            rep_ref = eng2.minimize(tol=10.0, max_iter=15)
-            eng2.close()
-            assert rep_cold["e_final"] == rep_ref["e_final"] and rep_cold["evaluations"] == rep_ref["evaluations"]
-        eng.close()
-    assert out[True][0]["e_final"] == out[False][0]["e_final"]  # the coarse stage is the same run
-    print("exact-stage iterations: cold", out[False][1]["iterations"], "warm", out[True][1]["iterations"])
-    assert out[True][1]["iterations"] <= out[False][1]["iterations"] + 5
