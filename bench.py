@@ -209,41 +209,60 @@ def oracle_full_evaluation(m) -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  nvidia-smi takes
+    a few hundred ms to deliver its first line, longer than a short timed region, so the sampler is started
+    ahead of it (before the warm-up); `mark_start` / `mark_end` bracket the timed region and the summary
+    keeps the samples that arrived inside the bracket (plus one sampling period)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 50
 
     def __init__(self, device: int):
         self.device = device
         self.proc = None
-        self.lines: list[str] = []
+        self.lines: list[tuple[float, str]] = []
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t_wait = time.perf_counter()
+            while not self.lines and time.perf_counter() - t_wait < 3.0:  # the first line: nvidia-smi is up
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc is not None:
+            time.sleep(1.5 * self.PERIOD_MS / 1e3)  # let the sample of the last period arrive
             self.proc.kill()  # exact PID we started
             self.proc.wait()
 
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        lo = self.t0 if self.t0 is not None else -1e30
+        hi = (self.t1 if self.t1 is not None else 1e30) + self.PERIOD_MS / 1e3
+        for when, ln in self.lines:
+            if not (lo <= when <= hi):
+                continue
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -393,12 +412,14 @@ def run_ours(opt):
         n = m.args.N_BEADS
 
         # ---- device-resident: K evaluations, CUDA events on the engine's stream -----------------
-        eng.evaluate_timed(W, flush_l2=True)
-        launches0 = eng.launch_count
-        barrier()
         with ClockSampler(local) as clk:
+            eng.evaluate_timed(W, flush_l2=True)
+            launches0 = eng.launch_count
+            barrier()
+            clk.mark_start()
             total_ms, pair_ms = eng.evaluate_timed(K, flush_l2=True)
             barrier()
+            clk.mark_end()
         launches = eng.launch_count - launches0
         coll_ms = eng.last_collective_ms if decomposed else 0.0
         total_ms, pair_ms_max, coll_ms = max_over_ranks([total_ms, pair_ms, coll_ms], device=dev)

@@ -236,11 +236,13 @@ int64_t mmm_launch_count(mmm_handle h);
 /* Pair-kernel selection (tests, A/B timing): 0 = automatic (Newton-3 kernel for the reference's
  * default forms, gather kernel otherwise), 1 = always the gather kernel. */
 int mmm_set_pair_kernel(mmm_handle h, int which);
-/* Coarse-stage surrogate for CHB (cut-off mode only, never the default, not the reference's potential):
- * the polynomial of model.py:416-419 evaluated between the centroids of clusters of <= 32 consecutive
- * same-chromosome beads instead of between all same-chromosome pairs (O(N) instead of the 1e9-pair
- * exact pass a truncated evaluation otherwise carries).  A proper potential with an exact gradient;
- * used by the opt-in two-stage minimisation (MIN_COARSE_CUTOFF), whose exact stage follows. */
+/* Coarse-stage far field (cut-off mode with the default forms only; never the default, not the
+ * reference's potential): the two long-range pieces a truncated evaluation misses — CHB's polynomial
+ * (model.py:416-419), which otherwise costs an exact pass over every same-chromosome pair, and the tail
+ * of the EV power law beyond the cut-off (model.py:199) — evaluated between the centroids of clusters of
+ * <= 32 consecutive same-chromosome beads (O(N + clusters^2)).  A proper potential with an exact gradient;
+ * used by the opt-in two-stage minimisation (MIN_COARSE_CUTOFF, MIN_COARSE_FAR_FIELD), whose exact stage
+ * follows. */
 int mmm_set_chb_surrogate(mmm_handle h, int on);
 /* mmm_minimize replays one captured CUDA graph per evaluation (per Morton-order period in cut-off
  * mode) instead of 6-7 separate launches; on = 0 goes back to plain launches (A/B timing, debugging).

@@ -172,7 +172,7 @@ _FIELDS: dict[str, tuple[Any, Any]] = {
     # engine extensions (not in the reference)
     "PAIR_CUTOFF": (float, 0.0),          # nm; 0 = exact all-pairs (the reference's NoCutoff)
     "MIN_COARSE_CUTOFF": (float, 0.0),    # nm; > 0: minimise with cut-off forces first, then finish on the exact potential
-    "MIN_COARSE_CHB": (str, "exact"),     # coarse stage only: the exact same-chromosome pass ("exact") or CHB on cluster centroids ("clusters", experimental)
+    "MIN_COARSE_FAR_FIELD": (str, "clusters"),  # coarse stage only: CHB and the EV tail beyond the cut-off between cluster centroids ("clusters"), or the exact CHB pass and no tail ("exact")
     "MIN_COARSE_MAX_ITERATIONS": (int, 20000),  # bound of the coarse stage (a truncated potential may never meet the tolerance)
     "MIN_TOLERANCE": (float, 10.0),       # kJ/mol/nm, OpenMM's minimizeEnergy default
     "MIN_MAX_ITERATIONS": (int, 0),       # 0 = until converged (OpenMM default)

@@ -440,7 +440,8 @@ static int ensure_scratch(mmm_system* h) {
   // (mmm_cutoff.cu), every other form on the cell-list gather kernel (mmm_cells.cu)
   const bool cut_n3 = mode == 3 && h->pair_kernel_pref != 1 && mmm_pair_n3_eligible(h);
   // coarse-stage surrogate: CHB on cluster centroids instead of the exact same-chromosome pass
-  const bool chb_cl = mode == 3 && h->chb_surrogate && h->pp.chb_form == MMM_CHB_POLYNOMIAL;
+  // (and the EV tail beyond the cut-off); default forms only
+  const bool chb_cl = mode == 3 && h->chb_surrogate && cut_n3;
   // pair_kernel_pref 2: the CTA-level CUT variant instead of the one-warp-per-item kernel (A/B timing)
   const bool cut_warp = cut_n3 && h->pair_kernel_pref != 2;
   const int sig = mode * 4 + (mode == 3 ? h->pp.chb_form + 1 : 0) + (cut_n3 ? 64 : 0) + (chb_cl ? 128 : 0) +

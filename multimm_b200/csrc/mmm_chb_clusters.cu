@@ -1,23 +1,28 @@
-// mmm_chb_clusters.cu — CHB on cluster centroids: the surrogate the COARSE stage of the opt-in
-// two-stage minimisation uses for the chromosomal-block term (model.py:386-451, polynomial form).
+// mmm_chb_clusters.cu — the far field on cluster centroids: what the COARSE stage of the opt-in
+// two-stage minimisation adds to the truncated pair pass (mmm_set_chb_surrogate; never in exact mode,
+// never by default in cut-off mode).
 //
-// CHB's polynomial dE (kC r^4 - r^3 + r^2) grows with r and cannot be truncated, so a cut-off
-// evaluation has to pay an exact all-pairs pass over every same-chromosome pair (1.08e9 pairs at
-// N = 2e5: as much as the whole truncated EV/SCB pass).  The term is weak (dE = 1e-4) and smooth,
-// and the coarse stage only has to come close to the minimum — the exact stage that follows meets
-// the stopping rule on the reference's potential.  So, when mmm_set_chb_surrogate(h, 1) is set in
-// cut-off mode, CHB is evaluated on CLUSTERS: runs of at most 32 consecutive beads of one chromosome
-// (the 32-bead tiles of the chain order, split where the chromosome changes),
-//     E_s = dE * sum_{T < T', same chromosome} n_T n_T' f(|c_T - c_T'|),   f(r) = kC r^4 - r^3 + r^2,
-// with c_T the centroid.  It is a proper potential (a function of the positions through the
-// centroids) whose gradient is exact: every bead of T feels -dE sum_T' n_T' f'(r)/r (c_T - c_T'), so
-// L-BFGS's line search stays consistent.  O(N + clusters^2 / chromosomes): 9e5 interactions at
-// N = 2e5 instead of 1.08e9.  Never used in exact mode, never by default.
+// A potential truncated at rc = 0.5 nm misses two long-range pieces of the reference's energy, and a
+// minimum of the truncated potential is not close to a minimum of the exact one without them:
+//   * CHB's polynomial dE (kC r^4 - r^3 + r^2) (model.py:416-419) grows with r and cannot be truncated
+//     at all — plain cut-off mode pays an exact pass over every same-chromosome pair for it (1.08e9
+//     pairs at N = 2e5, more than the truncated pass itself);
+//   * the tail of the EV power law beyond rc (model.py:199) is weak per pair but adds up to an outward
+//     pressure on the whole globule; without it the exact stage has to swell the structure, a collective
+//     move that costs L-BFGS hundreds of iterations (measured: 460-680 in five replicas of eight).
+// Both are smooth at these distances, so they are evaluated between CLUSTERS: runs of at most 32
+// consecutive beads of one chromosome (the 32-bead tiles of the chain order, split where the chromosome
+// changes), with c_T the centroid and n_T the size,
+//     E_far = sum_{T < U} n_T n_U [ same_chromosome(T, U) dE f(R) + S(R) eps (sigma / (R + r_s))^p ],
+//     R = |c_T - c_U|,  f(r) = kC r^4 - r^3 + r^2,  S = smoothstep from 0 at 0.7 rc to 1 at 1.3 rc
+// (bead pairs with r < rc are the truncated pass's; S hands over around rc).  It is a proper potential
+// — a function of the positions through the centroids — whose gradient is exact: every bead of T feels
+// -dE_far/dc_T / n_T, so L-BFGS's line search stays consistent.  O(N + clusters^2): 3.9e7 cluster pairs
+// at N = 2e5 instead of 1.08e9 + 2e10 bead pairs.
 //   k_cl_centroid   one warp per cluster: FP64 centroid of its beads             24 B read per bead
-//   k_cl_forces     one thread per cluster, loop over the clusters of its chromosome (FP64)
+//   k_cl_forces     one warp per cluster, lanes stride over all clusters (FP64), one energy slot per cluster
 // k_assemble adds the cluster's force to each of its beads.
 #include <algorithm>
-#include <numeric>
 
 #include "mmm_internal.cuh"
 
@@ -48,44 +53,73 @@ __global__ void __launch_bounds__(256) k_cl_centroid(const double* __restrict__ 
   }
 }
 
-// Thread q handles the q-th cluster in chromosome-sorted order; its chromosome's clusters are the
-// slots [range.x, range.y) of that order.
-__global__ void __launch_bounds__(128) k_cl_forces(const double* __restrict__ cen, const int* __restrict__ by_chrom,
-                                                   const int2* __restrict__ range, int ncl, double kc, double de,
-                                                   double* __restrict__ force, double* __restrict__ epair_slots,
-                                                   const int* __restrict__ skip) {
-  if (skip && *skip) return;
-  __shared__ double s_red[4];
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  double e = 0.0;
-  if (q < ncl) {
-    const int T = by_chrom[q];
-    const int2 rg = range[q];
-    const double cx = cen[4 * (size_t)T], cy = cen[4 * (size_t)T + 1], cz = cen[4 * (size_t)T + 2], nT = cen[4 * (size_t)T + 3];
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int p = rg.x; p < rg.y; ++p) {
-      if (p == q) continue;
-      const int U = by_chrom[p];
-      const double dx = cx - cen[4 * (size_t)U], dy = cy - cen[4 * (size_t)U + 1], dz = cz - cen[4 * (size_t)U + 2];
-      const double nU = cen[4 * (size_t)U + 3];
-      const double r2 = dx * dx + dy * dy + dz * dz, r = sqrt(r2);
-      e += nU * r2 * (kc * r2 - r + 1.0);                  // f(r)
-      const double g = -nU * (4.0 * kc * r2 - 3.0 * r + 2.0);  // -f'(r) / r
-      fx += g * dx; fy += g * dy; fz += g * dz;
+struct FarArgs {
+  const double* cen;     // [ncl][4] centroid, size
+  const int* chrom;      // [ncl]
+  int ncl;
+  int chb_on, ev_on;
+  double kc, de;                 // CHB
+  double eps, rs, sigma, power;  // EV
+  int ipower;                    // the power as an integer, 0 if it is not one
+  double r_lo, r_hi;             // S(R): 0 below r_lo, 1 above r_hi
+  double* force;         // [ncl][3]
+  double* epair_slots;   // [ncl][4]: EV tail in slot 0, CHB in slot 3
+  const int* skip;
+};
+
+__global__ void __launch_bounds__(256) k_cl_forces(const FarArgs A) {
+  if (A.skip && *A.skip) return;
+  const int lane = threadIdx.x & 31;
+  const int T = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (T >= A.ncl) return;
+  const double cx = A.cen[4 * (size_t)T], cy = A.cen[4 * (size_t)T + 1], cz = A.cen[4 * (size_t)T + 2], nT = A.cen[4 * (size_t)T + 3];
+  const int chT = A.chrom[T];
+  double fx = 0.0, fy = 0.0, fz = 0.0, e_ev = 0.0, e_chb = 0.0;
+  for (int U = lane; U < A.ncl; U += 32) {
+    if (U == T) continue;
+    const double dx = cx - A.cen[4 * (size_t)U], dy = cy - A.cen[4 * (size_t)U + 1], dz = cz - A.cen[4 * (size_t)U + 2];
+    const double nU = A.cen[4 * (size_t)U + 3];
+    const double r2 = dx * dx + dy * dy + dz * dz, r = sqrt(r2);
+    double g = 0.0;  // -dE/dR / R per unit n_T
+    if (A.chb_on && A.chrom[U] == chT) {
+      e_chb += nU * r2 * (A.kc * r2 - r + 1.0);
+      g -= A.de * nU * (4.0 * A.kc * r2 - 3.0 * r + 2.0);
     }
-    force[3 * (size_t)T] = de * fx;
-    force[3 * (size_t)T + 1] = de * fy;
-    force[3 * (size_t)T + 2] = de * fz;
-    e *= 0.5 * de * nT;  // every cluster pair is seen from both sides
+    if (A.ev_on && r > A.r_lo) {
+      const double w = 1.0 / (r + A.rs), sw = A.sigma * w;
+      double wp;
+      if (A.ipower == 6) { const double s2 = sw * sw; wp = s2 * s2 * s2; }
+      else if (A.ipower == 3) wp = sw * sw * sw;
+      else wp = pow(sw, A.power);
+      const double u = A.eps * wp, du = -A.power * u * w;
+      double sR = 1.0, dsR = 0.0;
+      if (r < A.r_hi) {
+        const double t = (r - A.r_lo) / (A.r_hi - A.r_lo);
+        sR = t * t * (3.0 - 2.0 * t);
+        dsR = 6.0 * t * (1.0 - t) / (A.r_hi - A.r_lo);
+      }
+      e_ev += nU * u * sR;
+      g -= nU * (du * sR + u * dsR) / r;
+    }
+    fx += g * dx; fy += g * dy; fz += g * dz;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double* slot = epair_slots + 4 * (size_t)blockIdx.x;
-    slot[0] = slot[1] = slot[2] = 0.0;
-    slot[3] = s_red[0] + s_red[1] + s_red[2] + s_red[3];  // the CHB energy slot
+  for (int o = 16; o > 0; o >>= 1) {
+    fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    e_ev += __shfl_xor_sync(0xffffffffu, e_ev, o);
+    e_chb += __shfl_xor_sync(0xffffffffu, e_chb, o);
+  }
+  if (lane == 0) {
+    A.force[3 * (size_t)T] = fx;
+    A.force[3 * (size_t)T + 1] = fy;
+    A.force[3 * (size_t)T + 2] = fz;
+    double* slot = A.epair_slots + 4 * (size_t)T;
+    slot[0] = 0.5 * nT * e_ev;  // every cluster pair is seen from both sides
+    slot[1] = 0.0;
+    slot[2] = 0.0;
+    slot[3] = 0.5 * nT * A.de * e_chb;
   }
 }
 
@@ -101,7 +135,7 @@ int upload_vec(mmm_system* h, T** dptr, const std::vector<T>& v) {
 
 }  // namespace
 
-int mmm_chb_clusters_blocks(const mmm_system* h) { return (h->n_clusters + 127) / 128; }
+int mmm_chb_clusters_blocks(const mmm_system* h) { return h->n_clusters; }  // one energy slot per cluster
 
 // Clusters are static (chromosome ids and the chain order do not change): built once per scratch.
 int mmm_chb_clusters_build(mmm_system* h) {
@@ -114,22 +148,11 @@ int mmm_chb_clusters_build(mmm_system* h) {
   }
   const int ncl = (int)start.size();
   start.push_back(n);
-  std::vector<int> by_chrom((size_t)ncl);
-  std::iota(by_chrom.begin(), by_chrom.end(), 0);
-  std::stable_sort(by_chrom.begin(), by_chrom.end(), [&](int a, int b) { return chrom[(size_t)a] < chrom[(size_t)b]; });
-  std::vector<int2> range((size_t)ncl);
-  for (int q = 0; q < ncl;) {
-    int e = q;
-    while (e < ncl && chrom[(size_t)by_chrom[(size_t)e]] == chrom[(size_t)by_chrom[(size_t)q]]) ++e;
-    for (int p = q; p < e; ++p) range[(size_t)p] = make_int2(q, e);
-    q = e;
-  }
   h->n_clusters = ncl;
   int rc;
   if ((rc = upload_vec(h, &h->d_cl_start, start))) return rc;
   if ((rc = upload_vec(h, &h->d_cl_of_bead, of_bead))) return rc;
-  if ((rc = upload_vec(h, &h->d_cl_by_chrom, by_chrom))) return rc;
-  if ((rc = upload_vec(h, &h->d_cl_range, range))) return rc;
+  if ((rc = upload_vec(h, &h->d_cl_by_chrom, chrom))) return rc;  // chromosome id of every cluster
   if (h->d_cl_cen) { cudaFree(h->d_cl_cen); h->d_cl_cen = nullptr; }
   if (h->d_cl_force) { cudaFree(h->d_cl_force); h->d_cl_force = nullptr; }
   MMM_CUDA(h, cudaMalloc((void**)&h->d_cl_cen, sizeof(double) * 4 * (size_t)ncl));
@@ -139,10 +162,22 @@ int mmm_chb_clusters_build(mmm_system* h) {
 
 int mmm_launch_chb_clusters(mmm_system* h, const int* d_skip) {
   const int ncl = h->n_clusters;
+  const PairParams& p = h->pp;
+  FarArgs A;
+  A.cen = h->d_cl_cen;
+  A.chrom = h->d_cl_by_chrom;
+  A.ncl = ncl;
+  A.chb_on = p.chb_form == MMM_CHB_POLYNOMIAL;
+  A.ev_on = p.ev_form == MMM_EV_POWERLAW && h->cutoff > 0.0;
+  A.kc = p.d_chb[0]; A.de = p.d_chb[1];
+  A.eps = p.d_ev[0]; A.rs = p.d_ev[1]; A.sigma = p.d_ev[2]; A.power = p.d_ev[3];
+  A.ipower = (A.power == 6.0) ? 6 : (A.power == 3.0 ? 3 : 0);
+  A.r_lo = 0.7 * h->cutoff; A.r_hi = 1.3 * h->cutoff;
+  A.force = h->d_cl_force;
+  A.epair_slots = h->d_epair + 4 * (size_t)h->cl_item0;
+  A.skip = d_skip;
   k_cl_centroid<<<(ncl + 7) / 8, 256, 0, h->stream>>>(h->d_x, h->d_cl_start, ncl, h->d_cl_cen, d_skip);
-  k_cl_forces<<<mmm_chb_clusters_blocks(h), 128, 0, h->stream>>>(h->d_cl_cen, h->d_cl_by_chrom, h->d_cl_range, ncl,
-                                                                 h->pp.d_chb[0], h->pp.d_chb[1], h->d_cl_force,
-                                                                 h->d_epair + 4 * (size_t)h->cl_item0, d_skip);
+  k_cl_forces<<<(ncl + 7) / 8, 256, 0, h->stream>>>(A);
   h->launches += 2;
   MMM_CUDA(h, cudaGetLastError());
   return MMM_OK;

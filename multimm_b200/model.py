@@ -286,10 +286,10 @@ class MultiMM:
             # 20 000); whatever it leaves undone the exact stage finishes.
             cap = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
             self.engine.set_cutoff(coarse)
-            # CHB cannot be truncated: the coarse stage carries its exact same-chromosome pass, or (opt-in,
-            # MIN_COARSE_CHB = clusters) evaluates it on cluster centroids — cheaper per evaluation, but the
-            # exact stage below may then have more left to do (profiles/r02_cutoff_mode.md)
-            self.engine.set_chb_surrogate(str(getattr(a, "MIN_COARSE_CHB", "exact")).lower() == "clusters")
+            # what a truncated potential misses at long range — CHB's polynomial and the EV tail — is
+            # evaluated between cluster centroids in the coarse stage (MIN_COARSE_FAR_FIELD = exact: the exact
+            # same-chromosome pass for CHB and no tail); the exact stage below is the reference's potential
+            self.engine.set_chb_surrogate(str(getattr(a, "MIN_COARSE_FAR_FIELD", "clusters")).lower() == "clusters")
             self.coarse_report = self.engine.minimize(tol=tol, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
             self.engine.set_cutoff(0.0)
             self.engine.set_chb_surrogate(False)

@@ -45,7 +45,7 @@ with tempfile.TemporaryDirectory() as tmp:
     tot, pair = eng.evaluate_timed(40, flush_l2=False)
     out["n3_warp_per_item_relaxed_chb_clusters"] = dict(ms_per_eval=tot / 40, cut_pass_ms=pair / 40)
     # two-stage minimisation (MIN_COARSE_CUTOFF): coarse stage on the truncated potential, exact stage after
-    for name, surrogate in (("two_stage_chb_exact", False),):
+    for name, surrogate in (("two_stage", False), ("two_stage_far_field_clusters", True)):
         eng.set_cutoff(rc)
         eng.set_chb_surrogate(surrogate)
         eng.set_positions(x0)
