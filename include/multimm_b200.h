@@ -193,7 +193,7 @@ int mmm_set_velocities(mmm_handle h, const double *v_nm_ps /* N x 3 */);
 int mmm_get_velocities(mmm_handle h, double *v_out);
 /* simulation.step(n) + getState(getEnergy=True), model.py:929-936: n steps enqueued back to back
  * (one fused force evaluation + one integrator launch each), energies read once at the end. */
-int mmm_md_run(mmm_handle h, int64_t n_steps, mmm_md_report *out);
+int mmm_md_run(mmm_handle h, int64_t n_steps, mmm_md_report *out /* NULL: no energies, no extra evaluation, no host read */);
 
 /* ---- structure report (plots.py:630-829 analyze_structure) ------------------------------------- */
 /* Mean of the full N x N distance matrix at the current positions (np.mean(cdist(V, V)),

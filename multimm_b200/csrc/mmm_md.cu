@@ -202,6 +202,10 @@ int mmm_md_run(mmm_handle h, int64_t n_steps, mmm_md_report* out) {
     k_md_step<<<blocks, 256, 0, h->stream>>>(A);
     h->launches++;
   }
+  if (!out) {  // no report wanted: the steps stay enqueued, nothing is evaluated or read back for it
+    MMM_CUDA(h, cudaGetLastError());
+    return MMM_OK;
+  }
   // energies at the final positions (potential) and velocities (kinetic)
   if ((rc = mmm_evaluate(h, nullptr))) return rc;
   if ((rc = mmm_launch_finalize_energy(h))) return rc;

@@ -193,7 +193,12 @@ class Engine:
         self._ck(self._lib.mmm_get_velocities(self._h, _p(out)))
         return out
 
-    def md_run(self, n_steps: int) -> dict:
+    def md_run(self, n_steps: int, want_report: bool = True) -> dict | None:
+        """n steps enqueued back to back.  want_report: one more force evaluation at the end for the potential
+        energy, the kinetic energy and a host read of both; without it nothing is evaluated or read back."""
+        if not want_report:
+            self._ck(self._lib.mmm_md_run(self._h, int(n_steps), None))
+            return None
         rep = MdReport()
         self._ck(self._lib.mmm_md_run(self._h, int(n_steps), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in MdReport._fields_}

@@ -290,7 +290,9 @@ class MultiMM:
             # evaluated between cluster centroids in the coarse stage (MIN_COARSE_FAR_FIELD = exact: the exact
             # same-chromosome pass for CHB and no tail); the exact stage below is the reference's potential
             self.engine.set_chb_surrogate(str(getattr(a, "MIN_COARSE_FAR_FIELD", "clusters")).lower() == "clusters")
-            self.coarse_report = self.engine.minimize(tol=tol, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
+            frac = float(getattr(a, "MIN_COARSE_TOLERANCE", 0.5) or 1.0)
+            self.coarse_report = self.engine.minimize(tol=tol * min(max(frac, 0.05), 1.0),
+                                                      max_iter=min(max_iter, cap) if max_iter > 0 else cap)
             self.engine.set_cutoff(0.0)
             self.engine.set_chb_surrogate(False)
             self.timings["coarse_iterations"] = int(self.coarse_report["iterations"])
@@ -330,9 +332,10 @@ class MultiMM:
         done = 0
         try:
             while done < (n_steps // every) * every:
-                rep = self.engine.md_run(chunk)
                 done += chunk
                 want_frame, want_dcd = done % every == 0, done % dcd_every == 0
+                # energies (one more force evaluation and a host read) only where a sample is recorded
+                rep = self.engine.md_run(chunk, want_report=want_frame)
                 if want_frame or want_dcd:
                     self.positions = self.engine.get_positions()
                 if want_dcd:

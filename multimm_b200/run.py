@@ -249,7 +249,10 @@ def replica_paths(out_path: str, n_ensemble: int) -> list[str]:
 
 
 def assign_replicas(n_ensemble: int, devices: list[int]) -> dict[int, list[int]]:
-    """Replica i -> devices[i mod G]."""
+    """The static plan, replica i -> devices[i mod G]: the order in which the GPUs take their FIRST
+    replicas.  run_ensemble hands the replicas out from one queue (a worker takes the next index when it
+    is free), because members differ a lot in cost (the exact stage of the two-stage minimisation takes 3
+    iterations in most replicas and hundreds in a few); with equal costs the two coincide."""
     plan: dict[int, list[int]] = {d: [] for d in devices}
     for i in range(n_ensemble):
         plan[devices[i % len(devices)]].append(i)
@@ -331,8 +334,39 @@ def run_replicas_on_device(params: dict, paths: list[str], todo: list[int], devi
                 emit(("error", dict(replica=-1, device=device, error=f"archive failed: {type(e).__name__}: {e}")))
 
 
-def _worker(params: dict, paths: list[str], todo: list[int], device: int, archive: bool, queue):
-    run_replicas_on_device(params, paths, todo, device, archive, queue.put)
+def _take(todo_queue):
+    """Replica indices from the shared queue until it is empty."""
+    import queue as _q
+
+    while True:
+        try:
+            yield todo_queue.get(timeout=1.0)  # (not get_nowait: the parent's feeder thread may still be flushing)
+        except _q.Empty:
+            return
+
+
+def _worker(params: dict, paths: list[str], todo_queue, device: int, archive: bool, queue):
+    # One GPU per worker process: with only its own device visible, CUDA initialisation does not touch
+    # the other seven (eight processes initialising an 8-GPU box at once took ~10 s each otherwise).
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if visible is None:
+        os.environ["CUDA_VISIBLE_DEVICES"] = str(device)
+        local = 0
+    else:  # the parent already runs under a restriction: `device` indexes into it
+        ids = [t for t in visible.split(",") if t.strip()]
+        if device < len(ids):
+            os.environ["CUDA_VISIBLE_DEVICES"] = ids[device]
+            local = 0
+        else:
+            local = device  # nothing sensible to narrow to: let mmm_create report it
+
+    def emit(msg):
+        kind, payload = msg
+        if isinstance(payload, dict) and "device" in payload:
+            payload["device"] = device  # the physical index, not the worker's local 0
+        queue.put((kind, payload))
+
+    run_replicas_on_device(params, paths, _take(todo_queue), local, archive, emit)
 
 
 def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -> list[dict]:
@@ -344,7 +378,6 @@ def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -
         devices = visible_devices(args)
     params = {k: v for k, v in args.model_dump().items()}
     paths = replica_paths(args.OUT_PATH, n)
-    plan = assign_replicas(n, devices)
     if len(devices) == 1:
         got = []
         run_replicas_on_device(params, paths, list(range(n)), devices[0], archive, got.append)
@@ -356,8 +389,11 @@ def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -
         return results
     ctx = mp.get_context("spawn")  # CUDA contexts must not be forked
     queue = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(params, paths, todo, dev, archive, queue))
-             for dev, todo in plan.items() if todo]
+    todo_queue = ctx.Queue()
+    for i in range(n):
+        todo_queue.put(i)
+    procs = [ctx.Process(target=_worker, args=(params, paths, todo_queue, dev, archive, queue))
+             for dev in devices[:n]]
     for p in procs:
         p.start()
     try:

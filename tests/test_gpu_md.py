@@ -108,3 +108,24 @@ def test_driver_runs_md_and_writes_the_reference_outputs(built_lib, tmp_path):
     assert np.allclose(frames[-1], last, atol=2e-3)
     rows = (out / "metadata/md_thermodynamics.tsv").read_text().strip().split("\n")
     assert len(rows) == 4 and rows[0].startswith("step")
+
+
+def test_md_steps_without_report_give_the_same_trajectory(built_lib):
+    """run_md asks for energies only where a sample is recorded (every chunk paid one more
+    force evaluation and a host read).  Chunks without a report must not change the trajectory."""
+    from common import make_case, to_engine
+
+    case = make_case(1500, n_chrom=2, seed=8)
+    out = []
+    for silent in (False, True):
+        eng = to_engine(case)
+        eng.md_configure("langevin", 0.001, 310.0, 0.5, 16427.889, seed=4)
+        eng.set_velocities_to_temperature(310.0, 4)
+        n0 = eng.launch_count
+        for _ in range(4):
+            eng.md_run(5, want_report=not silent)
+        rep = eng.md_run(5)
+        out.append((rep, eng.get_positions(), eng.launch_count - n0))
+        eng.close()
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+    assert out[1][2] < out[0][2]  # four evaluations (and their reductions) fewer

@@ -94,7 +94,8 @@ def test_ensemble_is_dealt_to_two_gpus(built_lib, tmp_path):
     args, _ = run.get_config(["-c", str(ini)])
     reports = run.run_ensemble(args, devices=[0, 1])
     assert [r["replica"] for r in reports] == [0, 1, 2, 3, 4]
-    assert [r["device"] for r in reports] == [0, 1, 0, 1, 0]
+    # one queue of replicas, a worker takes the next one when it is free: both GPUs worked, neither did it all
+    assert {r["device"] for r in reports} == {0, 1}
     for i in range(5):
         assert tarfile.is_tarfile(str(out / f"run_{i}.tar.gz"))
     assert len({round(r["e_final"], 3) for r in reports}) == 5
