@@ -464,7 +464,8 @@ def run_ours(opt):
             mine = ensemble_members(opt.workload, rank, world, local, tmp, opt.coarse_cutoff, opt.ensemble_members)
             slow = max_over_ranks([mine["wall_seconds"]], device=dev)[0]
             keep = ("replica", "seconds", "iterations", "evaluations", "e_final", "converged", "initialize_s",
-                    "forcefield_s", "minimize_s", "write_cif_s", "coarse_iterations", "coarse_seconds", "archive_inline_s")
+                    "forcefield_s", "minimize_s", "write_cif_s", "coarse_iterations", "coarse_seconds", "coarse_rounds",
+                    "exact_iterations", "archive_inline_s")
             members = world * opt.ensemble_members
             ens = dict(structures_per_hour=members * 3600.0 / slow, members=members, members_per_gpu=opt.ensemble_members,
                        gpus=world, slowest_rank_seconds=slow, unit="structures/hour",

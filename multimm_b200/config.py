@@ -173,7 +173,9 @@ _FIELDS: dict[str, tuple[Any, Any]] = {
     "PAIR_CUTOFF": (float, 0.0),          # nm; 0 = exact all-pairs (the reference's NoCutoff)
     "MIN_COARSE_CUTOFF": (float, 0.0),    # nm; > 0: minimise with cut-off forces first, then finish on the exact potential
     "MIN_COARSE_FAR_FIELD": (str, "clusters"),  # coarse stage only: CHB and the EV tail beyond the cut-off between cluster centroids ("clusters"), or the exact CHB pass and no tail ("exact")
-    "MIN_COARSE_TOLERANCE": (float, 0.5),  # coarse stage converges to this fraction of MIN_TOLERANCE (the two potentials' gradients differ a little: a margin lets the exact stage start inside its own tolerance)
+    "MIN_COARSE_TOLERANCE": (float, 1.0),  # first coarse round converges to this fraction of MIN_TOLERANCE; x 0.7 per further round
+    "MIN_COARSE_ROUNDS": (int, 4),         # coarse -> exact-probe rounds before the exact stage runs unbounded
+    "MIN_EXACT_PROBE_ITERATIONS": (int, 30),  # bound of the exact stage in all rounds but the last
     "MIN_COARSE_MAX_ITERATIONS": (int, 20000),  # bound of the coarse stage (a truncated potential may never meet the tolerance)
     "MIN_TOLERANCE": (float, 10.0),       # kJ/mol/nm, OpenMM's minimizeEnergy default
     "MIN_MAX_ITERATIONS": (int, 0),       # 0 = until converged (OpenMM default)

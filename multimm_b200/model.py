@@ -263,6 +263,52 @@ class MultiMM:
             self.engine.set_cutoff(cutoff)
         self.timings["forcefield_s"] = time.time() - t0
 
+    def _two_stage_minimize(self, tol: float, max_iter: int, coarse: float) -> dict:
+        """Opt-in two-stage minimisation (MIN_COARSE_CUTOFF > 0; not in the reference).  L-BFGS on a cheap
+        coarse potential — pair terms truncated at `coarse` nm, plus what truncation misses at long range
+        (CHB's polynomial, the EV tail) evaluated between cluster centroids (MIN_COARSE_FAR_FIELD = exact:
+        the exact same-chromosome pass for CHB and no tail) — gets close to a minimum at a fraction of the
+        cost per evaluation; the SAME stopping rule is then met on the exact all-pairs potential, so the
+        result satisfies exactly what minimizeEnergy() guarantees.
+
+        The two potentials' minima are close but not equal.  Most replicas need 0-15 exact iterations after
+        the coarse stage; some would need hundreds (measured: 10 of 64).  So the exact stage is first run as
+        a PROBE of MIN_EXACT_PROBE_ITERATIONS; if that does not converge, the coarse stage goes on from there
+        to a tighter tolerance (x 0.7 per round) and the exact probe is repeated; the last round's exact
+        stage is unbounded (or bounded by MIN_MAX_ITERATIONS).  The coarse stage itself is bounded
+        (MIN_COARSE_MAX_ITERATIONS): a truncated potential jumps at the cut-off, so L-BFGS on it is not
+        guaranteed to reach a gradient tolerance."""
+        a = self.args
+        cap = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
+        far = str(getattr(a, "MIN_COARSE_FAR_FIELD", "clusters")).lower() == "clusters"
+        frac = min(max(float(getattr(a, "MIN_COARSE_TOLERANCE", 1.0) or 1.0), 0.05), 1.0)
+        rounds = max(1, int(getattr(a, "MIN_COARSE_ROUNDS", 4) or 1))
+        probe = max(1, int(getattr(a, "MIN_EXACT_PROBE_ITERATIONS", 30) or 30))
+        c_it = c_ev = e_it = e_ev = 0
+        c_s = 0.0
+        rep = None
+        self.coarse_report = None
+        for r in range(rounds):
+            last = r == rounds - 1
+            self.engine.set_cutoff(coarse)
+            self.engine.set_chb_surrogate(far)
+            rep_c = self.engine.minimize(tol=tol * frac, max_iter=min(max_iter, cap) if max_iter > 0 else cap)
+            self.engine.set_cutoff(0.0)
+            self.engine.set_chb_surrogate(False)
+            self.coarse_report = rep_c if self.coarse_report is None else self.coarse_report
+            c_it += int(rep_c["iterations"]); c_ev += int(rep_c["evaluations"]); c_s += float(rep_c["wall_seconds"])
+            bound = max_iter if last else (min(probe, max_iter) if max_iter > 0 else probe)
+            rep = self.engine.minimize(tol=tol, max_iter=bound)
+            e_it += int(rep["iterations"]); e_ev += int(rep["evaluations"])
+            if rep["converged"] or rep["ls_status"] != 0:
+                break
+            frac *= 0.7
+        self.timings["coarse_iterations"], self.timings["coarse_evaluations"] = c_it, c_ev
+        self.timings["coarse_seconds"] = c_s
+        self.timings["coarse_rounds"] = r + 1
+        self.timings["exact_iterations"], self.timings["exact_evaluations"] = e_it, e_ev
+        return rep
+
     def min_energy(self):
         """model.py:859-897: minimise with OpenMM's defaults (10 kJ/mol/nm, unlimited iterations)
         and write model/MultiMM_minimized.cif (Angstrom)."""
@@ -277,27 +323,9 @@ class MultiMM:
             max_iter = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
             logger.warning(f"PAIR_CUTOFF > 0 with unlimited iterations: bounded at {max_iter} L-BFGS iterations")
         if coarse > 0.0 and final_cutoff == 0.0:
-            # opt-in two-stage minimisation (not in the reference): L-BFGS on the cell-list forces
-            # truncated at `coarse` gets close to a minimum at a fraction of the cost per
-            # evaluation; the SAME stopping rule is then met on the exact all-pairs potential, so the
-            # result satisfies exactly what minimizeEnergy() guarantees.
-            # A truncated potential is discontinuous at the cut-off, so this stage is not guaranteed
-            # to reach the gradient tolerance: it is bounded (MIN_COARSE_MAX_ITERATIONS, default
-            # 20 000); whatever it leaves undone the exact stage finishes.
-            cap = int(getattr(a, "MIN_COARSE_MAX_ITERATIONS", 20000) or 20000)
-            self.engine.set_cutoff(coarse)
-            # what a truncated potential misses at long range — CHB's polynomial and the EV tail — is
-            # evaluated between cluster centroids in the coarse stage (MIN_COARSE_FAR_FIELD = exact: the exact
-            # same-chromosome pass for CHB and no tail); the exact stage below is the reference's potential
-            self.engine.set_chb_surrogate(str(getattr(a, "MIN_COARSE_FAR_FIELD", "clusters")).lower() == "clusters")
-            frac = float(getattr(a, "MIN_COARSE_TOLERANCE", 0.5) or 1.0)
-            self.coarse_report = self.engine.minimize(tol=tol * min(max(frac, 0.05), 1.0),
-                                                      max_iter=min(max_iter, cap) if max_iter > 0 else cap)
-            self.engine.set_cutoff(0.0)
-            self.engine.set_chb_surrogate(False)
-            self.timings["coarse_iterations"] = int(self.coarse_report["iterations"])
-            self.timings["coarse_seconds"] = float(self.coarse_report["wall_seconds"])
-        self.report = self.engine.minimize(tol=tol, max_iter=max_iter)
+            self.report = self._two_stage_minimize(tol, max_iter, coarse)
+        else:
+            self.report = self.engine.minimize(tol=tol, max_iter=max_iter)
         self.positions = self.engine.get_positions()
         self.timings["minimize_s"] = time.time() - t0
         t1 = time.time()

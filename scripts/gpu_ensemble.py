@@ -35,7 +35,8 @@ def main():
     out = dict(n_ensemble=n_ens, gpus=len(devices), coarse_cutoff=coarse, wall_seconds=dt,
                structures_per_hour=3600.0 * n_ens / dt,
                per_replica=[{k: r.get(k) for k in ("replica", "device", "seconds", "iterations", "evaluations", "e_final",
-                                                   "converged", "minimize_s", "initialize_s", "forcefield_s", "write_cif_s")}
+                                                   "converged", "minimize_s", "initialize_s", "forcefield_s", "write_cif_s",
+                                                   "coarse_iterations", "coarse_rounds", "exact_iterations")}
                             for r in reports])
     print(json.dumps(out))
     json.dump(out, open(f"gpurun_out/ensemble_{n_ens}x{len(devices)}gpu_{coarse}.json", "w"), indent=1)

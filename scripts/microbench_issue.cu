@@ -206,6 +206,86 @@ __global__ void k_hot(float* out, float rs, int trips) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s + lo + hi;
 }
 
+// The hot body with the four register pairs of a j-bead processed PHASE BY PHASE (all r^2, then all
+// square roots, then all reciprocals, ...) instead of pair by pair: does the source order change what
+// ptxas's schedule achieves?
+__global__ void k_hot_phased(float* out, float rs, int trips) {
+  __shared__ float4 s_xy[32];
+  __shared__ float2 s_z[32];
+  if (threadIdx.x < 32) {
+    const float t = 0.1f * threadIdx.x;
+    s_xy[threadIdx.x] = make_float4(-t, -t, -2 * t, -2 * t);
+    s_z[threadIdx.x] = make_float2(-3 * t, -3 * t);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, a = lane >> 2, b = lane & 3;
+  u64 x2[4], y2[4], z2[4], fx[4], fy[4], fz[4];
+  for (int m = 0; m < 4; ++m) {
+    x2[m] = pk2(1.0f + lane + m, 1.5f + lane + m); y2[m] = pk2(2.0f + m, 2.5f + m); z2[m] = pk2(3.0f + m, 3.5f + m);
+    fx[m] = fy[m] = fz[m] = pk2(0.f, 0.f);
+  }
+  u64 ev2 = pk2(0.f, 0.f);
+  const u64 rs2 = pk2(rs, rs);
+  float jacc = 0.f;
+#pragma unroll 1
+  for (int t = 0; t < trips; ++t) {
+#pragma unroll 2
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int jl = (((2 * g + k) ^ a) << 2) | b;
+        const float4 nxy = s_xy[jl];
+        const float2 nz = s_z[jl];
+        const u64 njx = pk2(nxy.x, nxy.y), njy = pk2(nxy.z, nxy.w), njz = pk2(nz.x, nz.y);
+        u64 dx[4], dy[4], dz[4], r2[4], r[4], wr[4], fs[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          dx[m] = add2(x2[m], njx); dy[m] = add2(y2[m], njy); dz[m] = add2(z2[m], njz);
+          r2[m] = fma2(dz[m], dz[m], fma2(dy[m], dy[m], mul2(dx[m], dx[m])));
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          float p, q;
+          unpk2(r2[m], p, q);
+          r[m] = pk2(fsqrt(p), fsqrt(q));
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const u64 qq = fma2(rs2, r[m], r2[m]);
+          float p, q;
+          unpk2(qq, p, q);
+          wr[m] = pk2(frcp(p), frcp(q));
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const u64 w = mul2(r[m], wr[m]);
+          const u64 w2 = mul2(w, w);
+          const u64 w3 = mul2(w2, w);
+          const u64 wp = mul2(w3, w3);
+          ev2 = add2(ev2, wp);
+          fs[m] = mul2(wp, wr[m]);
+        }
+        u64 ax = pk2(0.f, 0.f), ay = ax, az = ax;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          fx[m] = fma2(fs[m], dx[m], fx[m]); fy[m] = fma2(fs[m], dy[m], fy[m]); fz[m] = fma2(fs[m], dz[m], fz[m]);
+          ax = fma2(fs[m], dx[m], ax); ay = fma2(fs[m], dy[m], ay); az = fma2(fs[m], dz[m], az);
+        }
+        float lo, hi;
+        unpk2(ax, lo, hi); jacc += lo + hi;
+        unpk2(ay, lo, hi); jacc += lo + hi;
+        unpk2(az, lo, hi); jacc += lo + hi;
+      }
+    }
+  }
+  float s = jacc, lo, hi;
+  for (int m = 0; m < 4; ++m) {
+    unpk2(fx[m], lo, hi); s += lo + hi; unpk2(fy[m], lo, hi); s += lo + hi; unpk2(fz[m], lo, hi); s += lo + hi;
+  }
+  unpk2(ev2, lo, hi);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s + lo + hi;
+}
+
 template <typename F>
 float time_ms(F launch) {
   cudaEvent_t a, b;
@@ -253,19 +333,20 @@ int main() {
   }
   for (int cfg = 0; cfg < 3; ++cfg) {
     const int threads = 256, per_sm = cfg == 0 ? 1 : (cfg == 1 ? 2 : 3), blocks = sms * per_sm, trips = 4096;
-    for (int variant = 0; variant < 5; ++variant) {
+    for (int variant = 0; variant < 6; ++variant) {
       float ms = time_ms([&] {
         if (variant == 0) k_hot<0><<<blocks, threads>>>(out, 0.05f, trips);
         else if (variant == 1) k_hot<1><<<blocks, threads>>>(out, 0.05f, trips);
         else if (variant == 2) k_hot<2><<<blocks, threads>>>(out, 0.05f, trips);
         else if (variant == 3) k_hot<3><<<blocks, threads>>>(out, 0.05f, trips);
-        else k_hot<4><<<blocks, threads>>>(out, 0.05f, trips);
+        else if (variant == 4) k_hot<4><<<blocks, threads>>>(out, 0.05f, trips);
+        else k_hot_phased<<<blocks, threads>>>(out, 0.05f, trips);
       });
       const double pairs = 64.0 * trips * (double)blocks * threads;
       const double cyc_pair = ms * 1e-3 * clk / (64.0 * trips * (per_sm * 8 / 4.0));
       printf("%-14s %9d %14.3f cycles per warp-pair per SMSP (floor 19); %.3e pairs/s\n",
              variant == 0 ? "hot sqrt+rcp" : variant == 1 ? "hot rsq+rcp" : variant == 2 ? "hot sqrt+rcp/2" :
-             variant == 3 ? "hot rsq+ser4" : "hot rsq+ser2", per_sm * 8, cyc_pair, pairs / (ms * 1e-3));
+             variant == 3 ? "hot rsq+ser4" : variant == 4 ? "hot rsq+ser2" : "hot phased", per_sm * 8, cyc_pair, pairs / (ms * 1e-3));
     }
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));

@@ -83,4 +83,5 @@ def test_only_documented_extra_fields():
     ours = set(SimulationConfig.model_fields)
     assert ref_fields <= ours
     assert ours - ref_fields == {"PAIR_CUTOFF", "MIN_TOLERANCE", "MIN_MAX_ITERATIONS", "MIN_COARSE_CUTOFF",
-                                 "MIN_COARSE_MAX_ITERATIONS", "MIN_COARSE_FAR_FIELD", "MIN_COARSE_TOLERANCE"}
+                                 "MIN_COARSE_MAX_ITERATIONS", "MIN_COARSE_FAR_FIELD", "MIN_COARSE_TOLERANCE", "MIN_COARSE_ROUNDS",
+                                 "MIN_EXACT_PROBE_ITERATIONS"}

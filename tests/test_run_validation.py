@@ -184,10 +184,13 @@ class TestWorkerLiveness:
 
 
 def test_coarse_stage_is_bounded(tmp_path, monkeypatch):
-    """MIN_COARSE_CUTOFF: the cut-off stage never runs unbounded, the exact stage keeps the user's bound."""
+    """MIN_COARSE_CUTOFF: the cut-off stage never runs unbounded; the exact stage is a bounded probe that hands
+    back to a tighter coarse stage when it does not converge, and runs with the user's bound (unbounded by
+    default) in the last round only."""
     from multimm_b200 import model
 
     calls = []
+    probe_converges = [True]
 
     class Eng:
         def __init__(self, n, device=0):
@@ -197,8 +200,9 @@ def test_coarse_stage_is_bounded(tmp_path, monkeypatch):
             def rec(*a, **k):
                 calls.append((name, a, k))
                 if name == "minimize":
+                    exact_probe = k["max_iter"] == 30
                     return dict(iterations=1, evaluations=2, e_initial=1.0, e_final=0.0, rms_force=1.0, wall_seconds=0.0,
-                                converged=1, ls_status=0)
+                                converged=int(probe_converges[0] or not exact_probe), ls_status=0)
                 if name == "get_positions":
                     import numpy as np
                     return np.zeros((self.n, 3))
@@ -208,13 +212,29 @@ def test_coarse_stage_is_bounded(tmp_path, monkeypatch):
             return rec
 
     monkeypatch.setattr(model, "Engine", Eng)
-    m = model.MultiMM(make_config(PLATFORM="B200", N_BEADS=6000, OUT_PATH=str(tmp_path / "o"), SAVE_PLOTS=False,
-                                  MIN_COARSE_CUTOFF=0.5))
-    m.set_radiuses(); m.initialize_simulation(); m.add_forcefield(); m.min_energy()
-    seq = [(n, a, k) for n, a, k in calls if n in ("set_cutoff", "minimize")]
+
+    def run():
+        calls.clear()
+        m = model.MultiMM(make_config(PLATFORM="B200", N_BEADS=6000, OUT_PATH=str(tmp_path / "o"), SAVE_PLOTS=False,
+                                      MIN_COARSE_CUTOFF=0.5))
+        m.set_radiuses(); m.initialize_simulation(); m.add_forcefield(); m.min_energy()
+        return m, [(n, a, k) for n, a, k in calls if n in ("set_cutoff", "minimize")]
+
+    m, seq = run()  # the exact probe converges: one round
     assert [n for n, _, _ in seq] == ["set_cutoff", "minimize", "set_cutoff", "minimize"]
     assert seq[0][1] == (0.5,) and seq[2][1] == (0.0,)
-    assert seq[1][2]["max_iter"] == 20000 and seq[3][2]["max_iter"] == 0
+    assert seq[1][2]["max_iter"] == 20000 and seq[1][2]["tol"] == 10.0
+    assert seq[3][2]["max_iter"] == 30 and seq[3][2]["tol"] == 10.0
+    assert m.timings["coarse_rounds"] == 1
+    probe_converges[0] = False  # it never does: four rounds, tighter coarse tolerance each, last exact stage unbounded
+    m, seq = run()
+    mins = [k for n, _, k in seq if n == "minimize"]
+    assert len(mins) == 8 and m.timings["coarse_rounds"] == 4
+    assert [k["max_iter"] for k in mins] == [20000, 30, 20000, 30, 20000, 30, 20000, 0]
+    tols = [k["tol"] for k in mins[0::2]]
+    assert tols[0] == 10.0 and all(abs(b / a - 0.7) < 1e-12 for a, b in zip(tols, tols[1:]))
+    assert all(k["tol"] == 10.0 for k in mins[1::2])  # the exact stage always at the user's tolerance
+    assert [a for n, a, _ in seq if n == "set_cutoff"] == [(0.5,), (0.0,)] * 4
 
 
 def test_ensemble_script_is_spawn_safe(monkeypatch):
