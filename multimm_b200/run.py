@@ -292,15 +292,27 @@ class Archiver:
         return spent
 
 
-def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool = True, archiver: Archiver | None = None) -> dict:
-    """One ensemble member: SHUFFLING_SEED = i, OUT_PATH = run_<i> (run.py:473-485).  With an
-    `archiver` the tar.gz is written in the background (the report names the file it will be)."""
+def build_replica(params: dict, i: int, run_path: str, device: int):
+    """Host side of one ensemble member up to the point where the GPU is needed: config with
+    SHUFFLING_SEED = i and OUT_PATH = run_<i> (run.py:473-476), output tree, input ingestion
+    (MultiMM.__init__: the loaders).  Pure host work: the driver runs it for member k + 1 on a background
+    thread while member k minimises."""
     from .model import MultiMM
 
     cfg = SimulationConfig(**{**params, "SHUFFLING_SEED": i, "OUT_PATH": run_path})
     os.makedirs(run_path, exist_ok=True)
     t0 = time.time()
     md = MultiMM(cfg, device=device)
+    md.timings["ingest_s"] = time.time() - t0
+    return md
+
+
+def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool = True, archiver: Archiver | None = None,
+                prebuilt=None) -> dict:
+    """One ensemble member (run.py:473-485).  With an `archiver` the tar.gz is written in the background
+    (the report names the file it will be); `prebuilt`: the member's MultiMM object from build_replica."""
+    t0 = time.time()
+    md = prebuilt if prebuilt is not None else build_replica(params, i, run_path, device)
     try:
         rep = md.run()
     finally:
@@ -317,16 +329,37 @@ def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool 
     return out
 
 
-def run_replicas_on_device(params: dict, paths: list[str], todo: list[int], device: int, archive: bool, emit):
-    """The replicas dealt to one GPU, one after another; archives overlap the next minimisation."""
+def run_replicas_on_device(params: dict, paths: list[str], todo, device: int, archive: bool, emit):
+    """The replicas one GPU takes, one after another.  Two things overlap the minimisation of member k:
+    the tar.gz of member k - 1 (Archiver) and the input ingestion of member k + 1 (build_replica on a
+    background thread; gzip, pandas' parsers and the engine's C calls release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     archiver = Archiver() if archive else None
+    prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mmm-ingest")
+    it = iter(todo)
+
+    def start_next():
+        i = next(it, None)
+        return None if i is None else (i, prefetch.submit(build_replica, params, i, paths[i], device))
+
     try:
-        for i in todo:
+        pending = start_next()
+        while pending is not None:
+            i, fut = pending
             try:
-                emit(("ok", run_replica(params, i, paths[i], device, archive, archiver)))
+                md = fut.result()
+            except Exception as e:
+                pending = start_next()
+                emit(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
+                continue
+            pending = start_next()  # member k + 1 is ingested while member k runs
+            try:
+                emit(("ok", run_replica(params, i, paths[i], device, archive, archiver, prebuilt=md)))
             except Exception as e:  # report and keep going with the next replica
                 emit(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
     finally:
+        prefetch.shutdown(wait=True)
         if archiver is not None:
             try:
                 archiver.wait()
