@@ -178,6 +178,7 @@ int mmm_minimize(mmm_handle h, double tol_kj_mol_nm, int64_t max_iter, mmm_min_r
 #define MMM_MD_LANGEVIN 0 /* mm.LangevinIntegrator(T, friction, dt)   model.py:781-787 */
 #define MMM_MD_VERLET 1   /* mm.VerletIntegrator(dt)                  model.py:770-772 */
 #define MMM_MD_BROWNIAN 2 /* mm.BrownianIntegrator(T, friction, dt)   model.py:801-807 */
+#define MMM_MD_AMD 3      /* mm.amd.AMDIntegrator(dt, alpha, E)       model.py:794-800 */
 typedef struct {
   int64_t step;        /* steps taken since mmm_md_configure */
   double potential;    /* kJ/mol at the current positions */
@@ -187,6 +188,9 @@ typedef struct {
 /* mass_amu: the single bead mass of forcefields/ff.xml:5 (16427.889). seed: noise stream. */
 int mmm_md_configure(mmm_handle h, int integrator, double dt_ps, double temperature_k,
                      double friction_per_ps, double mass_amu, uint64_t seed);
+/* The two globals of the accelerated-MD integrator (SIM_AMD_ALPHA, SIM_AMD_E; config.py:255-256:
+ * 100 and 1000 kJ/mol, the values a handle starts with).  Used by MMM_MD_AMD only. */
+int mmm_md_set_amd(mmm_handle h, double alpha_kj_mol, double e_boost_kj_mol);
 /* context.setVelocitiesToTemperature(T, seed), model.py:878. */
 int mmm_set_velocities_to_temperature(mmm_handle h, double temperature_k, uint64_t seed);
 int mmm_set_velocities(mmm_handle h, const double *v_nm_ps /* N x 3 */);

@@ -34,7 +34,7 @@ EXPORTS = (
     "mmm_energy_forces", "mmm_energy_forces_device", "mmm_evaluate_n", "mmm_evaluate_timed", "mmm_minimize",
     "mmm_launch_count", "mmm_set_graph", "mmm_set_chb_surrogate", "mmm_set_pair_kernel", "mmm_pair_kernel_in_use", "mmm_last_pair_kernel_ms", "mmm_get_cell_list", "mmm_get_cell_grid", "mmm_measure_fp32_peak",
     "mmm_dist_unique_id", "mmm_dist_init", "mmm_dist_emulate", "mmm_dist_last_exchange_ms", "mmm_dist_queue_mode",
-    "mmm_mean_pair_distance", "mmm_contact_map", "mmm_md_configure", "mmm_set_velocities_to_temperature", "mmm_set_velocities", "mmm_get_velocities", "mmm_md_run",
+    "mmm_mean_pair_distance", "mmm_contact_map", "mmm_md_configure", "mmm_md_set_amd", "mmm_set_velocities_to_temperature", "mmm_set_velocities", "mmm_get_velocities", "mmm_md_run",
 )
 
 
@@ -50,7 +50,7 @@ class MdReport(C.Structure):
     _fields_ = [("step", C.c_int64), ("potential", C.c_double), ("kinetic", C.c_double), ("temperature", C.c_double)]
 
 
-MD_INTEGRATORS = {"langevin": 0, "verlet": 1, "brownian": 2}
+MD_INTEGRATORS = {"langevin": 0, "verlet": 1, "brownian": 2, "amd": 3}
 
 
 class Error(RuntimeError):
@@ -116,6 +116,7 @@ def load():
         "mmm_mean_pair_distance": (i32, [vp, C.POINTER(dbl)]),
         "mmm_contact_map": (i32, [i32, vp, i64, i32, i32, vp, C.POINTER(dbl)]),
         "mmm_md_configure": (i32, [vp, i32, dbl, dbl, dbl, dbl, C.c_uint64]),
+        "mmm_md_set_amd": (i32, [vp, dbl, dbl]),
         "mmm_set_velocities_to_temperature": (i32, [vp, dbl, C.c_uint64]),
         "mmm_set_velocities": (i32, [vp, vp]),
         "mmm_get_velocities": (i32, [vp, vp]),

@@ -193,6 +193,7 @@ struct mmm_system {
   bool md_configured = false;
   int md_integrator = 0;
   double md_dt = 0.001, md_temperature = 310.0, md_gamma = 0.5, md_mass = 16427.889;
+  double md_amd_alpha = 100.0, md_amd_e = 1000.0;  // config.py:255-256
   uint64_t md_seed = 0;
   int64_t md_step = 0;
 

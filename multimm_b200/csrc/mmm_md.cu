@@ -9,6 +9,11 @@
 //   MMM_MD_VERLET    (VerletIntegrator)    leapfrog: v <- v + dt F/m;  x <- x + dt v
 //   MMM_MD_BROWNIAN  (BrownianIntegrator)  x <- x + dt/(gamma m) F + sqrt(2 kT dt/(gamma m)) N(0,1);
 //                                          v <- dx/dt
+//   MMM_MD_AMD       (amd.AMDIntegrator)   leapfrog on the boosted potential: with V the TOTAL potential
+//                                          energy at x(t), F' = F (alpha / (alpha + E - V))^2 where V <= E
+//                                          (CustomIntegrator's step(E - energy)), F' = F above it;
+//                                          v <- v + dt F'/m;  x <- x + dt v.  V is read on the device
+//                                          from the per-term energies of the same evaluation.
 // All beads carry the one mass of forcefields/ff.xml:5 (16427.889 amu) unless overridden.
 // Random numbers: Philox4x32-10, counter = (bead, step_lo, step_hi, stream), key = seed: the same
 // numbers whatever the launch geometry, reproducible, and restated in numpy by the tests.
@@ -56,13 +61,24 @@ struct MdArgs {
   double* x;
   double* v;
   const double* g;  // gradient (= -force) at x
+  const double* eterms;  // AMD: the MMM_NUM_TERMS per-term energies at x
+  double amd_alpha, amd_e;
 };
 
 __global__ void __launch_bounds__(256) k_md_step(const MdArgs A) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   double nrm[3] = {0.0, 0.0, 0.0};
-  if (A.integrator != MMM_MD_VERLET) normals3(A.seed, i, A.step, 1u, nrm);
+  if (A.integrator == MMM_MD_LANGEVIN || A.integrator == MMM_MD_BROWNIAN) normals3(A.seed, i, A.step, 1u, nrm);
+  double boost = 1.0;
+  if (A.integrator == MMM_MD_AMD) {
+    double pot = 0.0;
+    for (int t = 0; t < MMM_NUM_TERMS; ++t) pot += A.eterms[t];  // same order as the host's total
+    if (A.amd_e - pot >= 0.0) {
+      const double q = A.amd_alpha / (A.amd_alpha + A.amd_e - pot);
+      boost = q * q;
+    }
+  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double f = -A.g[3 * i + d];
@@ -74,6 +90,9 @@ __global__ void __launch_bounds__(256) k_md_step(const MdArgs A) {
       x += A.dt * v;
     } else if (A.integrator == MMM_MD_VERLET) {
       v += A.dt * A.inv_mass * f;
+      x += A.dt * v;
+    } else if (A.integrator == MMM_MD_AMD) {
+      v += A.dt * (f * boost) * A.inv_mass;
       x += A.dt * v;
     } else {  // Brownian
       const double dx = A.dt * A.inv_mass / A.gamma * f + sqrt(2.0 * A.kT * A.dt * A.inv_mass / A.gamma) * nrm[d];
@@ -124,8 +143,8 @@ extern "C" {
 int mmm_md_configure(mmm_handle h, int integrator, double dt_ps, double temperature_k, double friction_per_ps,
                      double mass_amu, uint64_t seed) {
   if (!h) return MMM_ERR_ARG;
-  if (integrator < MMM_MD_LANGEVIN || integrator > MMM_MD_BROWNIAN)
-    return mmm_fail(h, MMM_ERR_ARG, "Unknown SIM_INTEGRATOR_TYPE (supported: langevin, verlet, brownian)");
+  if (integrator < MMM_MD_LANGEVIN || integrator > MMM_MD_AMD)
+    return mmm_fail(h, MMM_ERR_ARG, "Unknown SIM_INTEGRATOR_TYPE (supported: langevin, verlet, brownian, amd)");
   if (!(dt_ps > 0.0) || !(mass_amu > 0.0) || temperature_k < 0.0 || friction_per_ps < 0.0)
     return mmm_fail(h, MMM_ERR_ARG, "mmm_md_configure: need dt > 0, mass > 0, temperature >= 0, friction >= 0");
   if (integrator == MMM_MD_BROWNIAN && !(friction_per_ps > 0.0))
@@ -138,6 +157,16 @@ int mmm_md_configure(mmm_handle h, int integrator, double dt_ps, double temperat
   h->md_seed = seed;
   h->md_step = 0;
   h->md_configured = true;
+  return MMM_OK;
+}
+
+int mmm_md_set_amd(mmm_handle h, double alpha_kj_mol, double e_boost_kj_mol) {
+  if (!h) return MMM_ERR_ARG;
+  // alpha = 0 makes the boost factor 0/0 at V = E; OpenMM leaves that to the user, a handle refuses it
+  if (!isfinite(alpha_kj_mol) || !isfinite(e_boost_kj_mol) || !(alpha_kj_mol > 0.0))
+    return mmm_fail(h, MMM_ERR_ARG, "mmm_md_set_amd: need alpha > 0 and a finite E");
+  h->md_amd_alpha = alpha_kj_mol;
+  h->md_amd_e = e_boost_kj_mol;
   return MMM_OK;
 }
 
@@ -195,9 +224,13 @@ int mmm_md_run(mmm_handle h, int64_t n_steps, mmm_md_report* out) {
   A.x = h->d_x;
   A.v = h->d_v;
   A.g = h->d_g;
+  A.eterms = h->d_eterms;
+  A.amd_alpha = h->md_amd_alpha;
+  A.amd_e = h->md_amd_e;
   const unsigned blocks = (unsigned)((h->n + 255) / 256);
   for (int64_t s = 0; s < n_steps; ++s) {
     if ((rc = mmm_evaluate(h, nullptr))) return rc;  // forces at x(t)
+    if (A.integrator == MMM_MD_AMD && (rc = mmm_launch_finalize_energy(h))) return rc;  // V(x(t)) for the boost
     A.step = h->md_step++;
     k_md_step<<<blocks, 256, 0, h->stream>>>(A);
     h->launches++;

@@ -172,12 +172,17 @@ class Engine:
 
     # -- MD relaxation ----------------------------------------------------------------------------
     def md_configure(self, integrator="langevin", dt_ps=0.001, temperature_k=310.0, friction_per_ps=0.5,
-                     mass_amu=16427.889, seed=0):
+                     mass_amu=16427.889, seed=0, amd_alpha=None, amd_e=None):
+        """amd_alpha / amd_e: the two globals of mm.amd.AMDIntegrator (model.py:796-800), kJ/mol; used by
+        the "amd" integrator only (a handle starts with the reference's defaults, 100 and 1000)."""
         kind = _lib.MD_INTEGRATORS.get(integrator, integrator) if isinstance(integrator, str) else int(integrator)
         if not isinstance(kind, int):
-            raise ValueError(f"Unknown SIM_INTEGRATOR_TYPE: {integrator} (supported: langevin, verlet, brownian)")
+            raise ValueError(f"Unknown SIM_INTEGRATOR_TYPE: {integrator} (supported: {', '.join(_lib.MD_INTEGRATORS)})")
         self._ck(self._lib.mmm_md_configure(self._h, kind, float(dt_ps), float(temperature_k), float(friction_per_ps),
                                             float(mass_amu), int(seed)))
+        if amd_alpha is not None or amd_e is not None:
+            self._ck(self._lib.mmm_md_set_amd(self._h, float(100.0 if amd_alpha is None else amd_alpha),
+                                              float(1000.0 if amd_e is None else amd_e)))
 
     def set_velocities_to_temperature(self, temperature_k: float, seed: int = 0):
         self._ck(self._lib.mmm_set_velocities_to_temperature(self._h, float(temperature_k), int(seed)))

@@ -348,7 +348,8 @@ class MultiMM:
         dt = _f(a.SIM_INTEGRATOR_STEP)  # ps
         temp = _f(a.SIM_TEMPERATURE)
         seed = int(a.SHUFFLING_SEED)
-        self.engine.md_configure(kind, dt, temp, float(a.SIM_FRICTION_COEFF), loaders.BEAD_MASS, seed)
+        self.engine.md_configure(kind, dt, temp, float(a.SIM_FRICTION_COEFF), loaders.BEAD_MASS, seed,
+                                 amd_alpha=_f(a.SIM_AMD_ALPHA), amd_e=_f(a.SIM_AMD_E))  # model.py:796-800
         self.engine.set_velocities_to_temperature(temp, seed)  # model.py:878
         self.md_history = {"step": [], "potential": [], "kinetic": [], "total": [], "temperature": []}
         n_steps, every = int(a.SIM_N_STEPS), max(1, int(a.SIM_SAMPLING_STEP))

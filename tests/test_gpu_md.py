@@ -64,6 +64,47 @@ def test_steps_match_numpy_restatement(built_lib, integrator):
     eng.close()
 
 
+@pytest.mark.parametrize("e_boost", ["above", "below"])
+def test_amd_steps_match_numpy_restatement(built_lib, e_boost):
+    """[OpenMM] amd.AMDIntegrator (model.py:794-800): leapfrog with the force scaled by
+    (alpha / (alpha + E - V))^2 while the total potential energy V is at or below E, unscaled above it.
+    Three steps against numpy with the ORACLE's forces and energies, both branches of step(E - V)."""
+    case = make_case(400, n_chrom=2, seed=6, noise=0.02)
+    sysd = to_oracle(case)
+    eng = to_engine(case)
+    e0 = O.energy_forces(sysd, case["x"])[0].sum()
+    alpha = 0.05 * abs(e0)
+    e_thr = e0 + 0.3 * abs(e0) if e_boost == "above" else e0 - 0.3 * abs(e0)
+    dt, temp, seed = 0.002, 310.0, 12
+    eng.md_configure("amd", dt, temp, 0.0, MASS, seed, amd_alpha=alpha, amd_e=e_thr)
+    eng.set_velocities_to_temperature(temp, seed)
+    x, v = case["x"].copy(), eng.get_velocities()
+    boosts = []
+    for step in range(3):
+        e_terms, f = O.energy_forces(sysd, x)
+        pot = e_terms.sum()
+        boost = (alpha / (alpha + e_thr - pot)) ** 2 if e_thr - pot >= 0 else 1.0
+        boosts.append(boost)
+        v = v + dt * f * boost / MASS
+        x = x + dt * v
+    assert all(b < 0.05 for b in boosts) if e_boost == "above" else boosts == [1.0] * 3
+    rep = eng.md_run(3)
+    assert rep["step"] == 3
+    assert np.abs(eng.get_positions() - x).max() < 1e-7
+    assert np.abs(eng.get_velocities() - v).max() < 1e-4 * np.abs(v).max()
+    eng.close()
+
+
+def test_amd_defaults_are_the_reference_config_values_and_bad_alpha_is_refused(built_lib):
+    case = make_case(300, n_chrom=1, seed=2, terms=("EV", "BOND"))
+    eng = to_engine(case)
+    eng.md_configure("amd", 0.001, 310.0, 0.0, MASS, 1)  # SIM_AMD_ALPHA = 100, SIM_AMD_E = 1000 (config.py:255-256)
+    assert eng.md_run(2)["step"] == 2
+    with pytest.raises(Exception, match="alpha"):
+        eng.md_configure("amd", 0.001, 310.0, 0.0, MASS, 1, amd_alpha=0.0, amd_e=10.0)
+    eng.close()
+
+
 def test_verlet_conserves_energy(built_lib):
     case = make_case(1500, n_chrom=2, seed=9, terms=("EV", "SCB", "SC", "BOND", "LOOP", "ANGLE"))
     eng = to_engine(case)

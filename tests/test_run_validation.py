@@ -278,12 +278,13 @@ def test_two_worker_ensemble_reports_instead_of_hanging(tmp_path):
 
 
 def test_unavailable_integrator_and_platform_fail_before_any_work():
-    """A config asking for an integrator this engine does not have (amd, the two variable-step ones)
+    """A config asking for an integrator this engine does not have (the two variable-step ones)
     used to run the whole minimisation first and fail in run_md; a PLATFORM that is no platform at all
     used to fail after the loaders had run.  Both are cross-field checks now."""
     from multimm_b200.run import args_tests
 
-    for kind in ("amd", "variable_verlet", "variable_langevin"):
+    args_tests(make_config(SIM_RUN_MD=True, SIM_INTEGRATOR_TYPE="amd"))
+    for kind in ("variable_verlet", "variable_langevin"):
         with pytest.raises(ValueError, match="SIM_INTEGRATOR_TYPE"):
             args_tests(make_config(SIM_RUN_MD=True, SIM_INTEGRATOR_TYPE=kind))
         args_tests(make_config(SIM_RUN_MD=False, SIM_INTEGRATOR_TYPE=kind))  # irrelevant without MD
