@@ -143,6 +143,7 @@ int mmm_destroy(mmm_handle h) {
   if (h->h_done) cudaFreeHost(h->h_done);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->d_flush) cudaFree(h->d_flush);
+  if (h->d_fout) cudaFree(h->d_fout);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -310,11 +311,19 @@ int mmm_set_cutoff(mmm_handle h, double rc_nm) {
 
 // ---- state -----------------------------------------------------------------------------
 static int set_center_from_host(mmm_system* h, const double* x) {
-  // arithmetic mean in index order: identical on the oracle side, so the FP32 copies agree bit for bit
-  double c[3] = {0, 0, 0};
-  for (int64_t i = 0; i < h->n; ++i)
-    for (int d = 0; d < 3; ++d) c[d] += x[3 * i + d];
-  for (int d = 0; d < 3; ++d) c[d] /= (double)h->n;
+  // arithmetic mean in index order: identical on the oracle side, so the FP32 copies agree bit for bit.
+  // The same pass is the finiteness check: a NaN or an infinity anywhere leaves a non-finite sum.
+  double c0 = 0, c1 = 0, c2 = 0;
+  for (int64_t i = 0; i < h->n; ++i) {
+    c0 += x[3 * i];
+    c1 += x[3 * i + 1];
+    c2 += x[3 * i + 2];
+  }
+  if (!isfinite(c0) || !isfinite(c1) || !isfinite(c2)) {
+    cudaStreamSynchronize(h->stream);  // the caller's buffer may still be in flight
+    return mmm_fail(h, MMM_ERR_NUMERIC, "non-finite coordinate");
+  }
+  double c[3] = {c0 / (double)h->n, c1 / (double)h->n, c2 / (double)h->n};
   MMM_CUDA(h, cudaMemcpyAsync(h->d_center, c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
   MMM_CUDA(h, cudaStreamSynchronize(h->stream));
   return MMM_OK;
@@ -324,11 +333,13 @@ int mmm_set_positions(mmm_handle h, const double* xyz) {
   if (!h) return MMM_ERR_ARG;
   REQUIRE(h, xyz, "mmm_set_positions: NULL");
   cudaSetDevice(h->device);
-  for (int64_t q = 0; q < 3 * h->n; ++q)
-    if (!isfinite(xyz[q])) return mmm_fail(h, MMM_ERR_NUMERIC, "mmm_set_positions: non-finite coordinate");
+  // the copy (asynchronous from pinned memory) overlaps the host's one pass over the coordinates
   MMM_CUDA(h, cudaMemcpyAsync(h->d_x, xyz, sizeof(double) * 3 * h->n, cudaMemcpyHostToDevice, h->stream));
   int rc = set_center_from_host(h, xyz);
-  if (rc) return rc;
+  if (rc) {
+    h->positions_set = false;  // d_x holds the rejected coordinates
+    return rc;
+  }
   h->positions_set = true;
   h->sort_age = 0;  // cut-off mode: new positions from outside, rebuild the Morton order
   return MMM_OK;
@@ -580,6 +591,11 @@ int mmm_evaluate(mmm_system* h, const int* d_skip) {
   return mmm_launch_assemble(h, d_skip);
 }
 
+static __global__ void __launch_bounds__(256) k_negate(int64_t n3, const double* __restrict__ g, double* __restrict__ f) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e < n3) f[e] = -g[e];
+}
+
 static int check_ready(mmm_system* h) {
   if (!h->positions_set) return mmm_fail(h, MMM_ERR_STATE, "positions were never set");
   return MMM_OK;
@@ -611,10 +627,13 @@ int mmm_energy_forces(mmm_handle h, double* e_terms, double* forces) {
   if (!h) return MMM_ERR_ARG;
   int rc = mmm_energy_forces_device(h, e_terms, nullptr);
   if (rc) return rc;
-  if (forces) {
-    MMM_CUDA(h, cudaMemcpyAsync(forces, h->d_g, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (forces) {  // d_g holds the gradient: negated on the device, not by a host pass over 24 N bytes
+    if (!h->d_fout) MMM_CUDA(h, cudaMalloc((void**)&h->d_fout, sizeof(double) * 3 * (size_t)h->n));
+    k_negate<<<(unsigned)((3 * h->n + 255) / 256), 256, 0, h->stream>>>(3 * h->n, h->d_g, h->d_fout);
+    h->launches++;
+    MMM_CUDA(h, cudaGetLastError());
+    MMM_CUDA(h, cudaMemcpyAsync(forces, h->d_fout, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToHost, h->stream));
     MMM_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int64_t q = 0; q < 3 * h->n; ++q) forces[q] = -forces[q];  // d_g holds the gradient
   }
   return MMM_OK;
 }

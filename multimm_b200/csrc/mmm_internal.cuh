@@ -241,6 +241,7 @@ struct mmm_system {
   std::vector<cudaEvent_t> ev_pool;  // per-launch event pairs while a timed batch runs
   int ev_cursor = -1;                // -1: not collecting
   void* d_flush = nullptr;           // 256 MiB L2-flush scratch (bench only)
+  double* d_fout = nullptr;          // [3n] forces (= -gradient) staged for mmm_energy_forces' host copy
   float last_pair_ms = 0.f;
 };
 

@@ -37,6 +37,29 @@ def test_all_default_terms(built_lib, n, n_chrom):
     _check(make_case(n, n_chrom=n_chrom, seed=n))
 
 
+def test_non_finite_coordinates_are_refused_and_host_forces_are_minus_the_gradient(built_lib):
+    """mmm_set_positions checks finiteness in the same host pass that forms the centre; the forces
+    mmm_energy_forces copies to the host are negated on the device (no host pass over them)."""
+    from multimm_b200 import Error
+
+    case = make_case(700, n_chrom=2, seed=12)
+    eng = to_engine(case)
+    e, f = eng.energy_forces()
+    for bad in (np.nan, np.inf, -np.inf):
+        x = case["x"].copy()
+        x[311, 1] = bad
+        with pytest.raises(Error, match="non-finite"):
+            eng.set_positions(x)
+        with pytest.raises(Error):  # the rejected coordinates are not evaluated
+            eng.energy_forces()
+    eng.set_positions(case["x"])
+    e2, f2 = eng.energy_forces()
+    assert np.array_equal(e, e2) and np.array_equal(f, f2)
+    f_ref = O.energy_forces(to_oracle(case), case["x"])[1]
+    assert force_rel_err(f, f_ref) <= F_TOL  # the sign in particular
+    eng.close()
+
+
 def test_s1_region_terms(built_lib):
     """configs[0]: specific-region model, {bonds, angles, loops, EV}."""
     _check(make_case(10000, terms=("EV", "BOND", "LOOP", "ANGLE"), seed=3))
