@@ -119,8 +119,7 @@ struct N3Args {
   const TileInfo* tiles;
   unsigned long long* facc;  // [3][npad] fixed-point force, units 2^-24 kJ/mol/nm
   double* epair;             // [n_items][4]
-  const int2* items;         // (i-block, first j-stage | number of stages << 24 | half << 29): half 1 / 2 =
-                             // only tiles 0-3 / 4-7 of the item's single stage (small systems), 0 = all
+  const int2* items;         // (i-block, first j-stage | number of stages << 24)
   int* counter;
   const int* skip;
   int64_t npad;
@@ -553,8 +552,7 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
     const int item = A.item_first + s_item * A.item_stride;
     if (item >= A.n_items) break;
     const int2 it = A.items[item];
-    const int iblk = it.x, js0 = it.y & 0xFFFFFF, cnt = (it.y >> 24) & 31, half = (it.y >> 29) & 3;
-    const int step0 = half == 2 ? N3_STEPS / 2 : 0, step1 = half == 1 ? N3_STEPS / 2 : N3_STEPS;
+    const int iblk = it.x, js0 = it.y & 0xFFFFFF, cnt = it.y >> 24;
     const int64_t ibase = (int64_t)iblk * N3_IB;
     const int iw = warp * 64 + a * 8;  // first of this lane's i-beads within the block
 
@@ -670,7 +668,7 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
               if (CUT && !(d2 < c.cut2)) my_class = -1;      // every pair of the tile pair is beyond the cut-off
             }
           }
-          for (int step = step0; step < step1; ++step) {
+          for (int step = 0; step < N3_STEPS; ++step) {
             const int cls = __shfl_sync(0xffffffffu, my_class, step);
             if (cls < 0) continue;
             const float4* sj = s_j[buf] + step * MMM_TILE;
@@ -799,6 +797,10 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
 // forces per item, both as 64-bit fixed point through the sort permutation; energies and the pair
 // count leave as 64-bit fixed point too (2^-20 kJ/mol), so that every sum is associative and the
 // result does not depend on which warp ran which item.
+// (Measured and dropped, profiles/r02_cutoff_mode.md: testing all 64 tiles of a chunk with two ballots and
+// fetching the next surviving tile while the current one is evaluated — 0.811 against 0.805 ms, the pass is
+// bound by the arithmetic of its candidate pairs, not by these round trips; 128-thread CTAs at 96 registers
+// (5 per SM instead of 2 x 256 threads at 128): 0.871 ms.)
 constexpr double CW_EFIXED = 1048576.0;  // 2^20
 constexpr int CW_CHUNK = 8;              // stages per item: fine enough that the items near the diagonal (where the work is) spread over all warps
 
@@ -1111,9 +1113,9 @@ int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, bool chb_only) {
   const int64_t target_items = (int64_t)h->sm_count * 2 * 48;
   int64_t cj = pairs / target_items;
   cj = cj < 1 ? 1 : (cj > 16 ? 16 : cj);
-  // Small systems (S1: 420 stage pairs for 296 resident CTAs, i.e. two uneven waves): every stage pair
-  // becomes two items of four tiles each, so that the last wave is half as long.
-  const bool halves = cj == 1 && pairs < (int64_t)h->sm_count * 2 * 3;
+  // (Measured and dropped: half-stage items for small systems — S1 has 420 stage pairs for 296 resident
+  // CTAs — cost 108.7 against 101 us per evaluation: the per-item i-side emission and energy reduction
+  // outweigh the shorter last wave.)
   items.clear();
   for (int64_t i = 0; i < nib; ++i) {
     int64_t js = 2 * i;
@@ -1121,12 +1123,7 @@ int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, bool chb_only) {
       if (!wanted(i, js)) { ++js; continue; }
       int64_t cnt = 1;
       while (cnt < cj && js + cnt < njs && wanted(i, js + cnt)) ++cnt;
-      if (halves) {
-        items.push_back(make_int2((int)i, (int)(js | (1 << 24) | (1 << 29))));
-        items.push_back(make_int2((int)i, (int)(js | (1 << 24) | (2 << 29))));
-      } else {
-        items.push_back(make_int2((int)i, (int)(js | (cnt << 24))));
-      }
+      items.push_back(make_int2((int)i, (int)(js | (cnt << 24))));
       js += cnt;
     }
   }
