@@ -22,6 +22,10 @@
 //   k_cl_centroid   one warp per cluster: FP64 centroid of its beads             24 B read per bead
 //   k_cl_forces     one warp per cluster, lanes stride over all clusters (FP64), one energy slot per cluster
 // k_assemble adds the cluster's force to each of its beads.
+// (Measured and dropped, calls 18 / 19: FP32 pair arithmetic on FP64 deltas in k_cl_forces.  The coarse
+// evaluation went from 1.161 to 1.095 ms, but 5 of 16 ensemble members then needed a second coarse round
+// against 1 of 16 — the rounding noise of the FP32 pair energies, ~1 kJ/mol in the total, is of the order
+// of L-BFGS's last decreases, and the coarse stage's line search gives up early.  FP64 stays.)
 #include <algorithm>
 
 #include "mmm_internal.cuh"
@@ -67,42 +71,65 @@ struct FarArgs {
   const int* skip;
 };
 
+// One warp per cluster T; the CTA's 8 warps walk all clusters U together, 256 at a time through shared
+// memory (as planes: conflict-free).  Without the staging every warp streamed the whole centroid table
+// (200 KB at N = 2e5) from L2 on its own: 1.4 GB per launch, and the kernel was L2-bound at 0.30 ms; lane l
+// still takes U = l, l + 32, ... in ascending order (same summation order as before).
+constexpr int CL_CHUNK = 256;
 __global__ void __launch_bounds__(256) k_cl_forces(const FarArgs A) {
+  __shared__ double s_x[CL_CHUNK], s_y[CL_CHUNK], s_z[CL_CHUNK], s_n[CL_CHUNK];
+  __shared__ int s_c[CL_CHUNK];
   if (A.skip && *A.skip) return;
-  const int lane = threadIdx.x & 31;
-  const int T = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (T >= A.ncl) return;
-  const double cx = A.cen[4 * (size_t)T], cy = A.cen[4 * (size_t)T + 1], cz = A.cen[4 * (size_t)T + 2], nT = A.cen[4 * (size_t)T + 3];
-  const int chT = A.chrom[T];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int T = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  const bool live = T < A.ncl;
+  const int Tc = live ? T : 0;
+  const double cx = A.cen[4 * (size_t)Tc], cy = A.cen[4 * (size_t)Tc + 1], cz = A.cen[4 * (size_t)Tc + 2], nT = A.cen[4 * (size_t)Tc + 3];
+  const int chT = A.chrom[Tc];
+  const double inv_band = 1.0 / (A.r_hi - A.r_lo);
   double fx = 0.0, fy = 0.0, fz = 0.0, e_ev = 0.0, e_chb = 0.0;
-  for (int U = lane; U < A.ncl; U += 32) {
-    if (U == T) continue;
-    const double dx = cx - A.cen[4 * (size_t)U], dy = cy - A.cen[4 * (size_t)U + 1], dz = cz - A.cen[4 * (size_t)U + 2];
-    const double nU = A.cen[4 * (size_t)U + 3];
-    const double r2 = dx * dx + dy * dy + dz * dz, r = sqrt(r2);
-    double g = 0.0;  // -dE/dR / R per unit n_T
-    if (A.chb_on && A.chrom[U] == chT) {
-      e_chb += nU * r2 * (A.kc * r2 - r + 1.0);
-      g -= A.de * nU * (4.0 * A.kc * r2 - 3.0 * r + 2.0);
+  for (int base = 0; base < A.ncl; base += CL_CHUNK) {
+    __syncthreads();  // the previous chunk has been consumed
+    if (base + tid < A.ncl) {
+      const double2 c01 = *reinterpret_cast<const double2*>(A.cen + 4 * (size_t)(base + tid));
+      const double2 c23 = *reinterpret_cast<const double2*>(A.cen + 4 * (size_t)(base + tid) + 2);
+      s_x[tid] = c01.x; s_y[tid] = c01.y; s_z[tid] = c23.x; s_n[tid] = c23.y;
+      s_c[tid] = A.chrom[base + tid];
     }
-    if (A.ev_on && r > A.r_lo) {
-      const double w = 1.0 / (r + A.rs), sw = A.sigma * w;
-      double wp;
-      if (A.ipower == 6) { const double s2 = sw * sw; wp = s2 * s2 * s2; }
-      else if (A.ipower == 3) wp = sw * sw * sw;
-      else wp = pow(sw, A.power);
-      const double u = A.eps * wp, du = -A.power * u * w;
-      double sR = 1.0, dsR = 0.0;
-      if (r < A.r_hi) {
-        const double t = (r - A.r_lo) / (A.r_hi - A.r_lo);
-        sR = t * t * (3.0 - 2.0 * t);
-        dsR = 6.0 * t * (1.0 - t) / (A.r_hi - A.r_lo);
+    __syncthreads();
+    if (!live) continue;
+    const int cnt = min(CL_CHUNK, A.ncl - base);
+    for (int q = lane; q < cnt; q += 32) {
+      if (base + q == T) continue;
+      const double dx = cx - s_x[q], dy = cy - s_y[q], dz = cz - s_z[q];
+      const double nU = s_n[q];
+      // one reciprocal square root instead of a square root and a division by r (the kernel is FP64-bound)
+      const double r2 = fmax(dx * dx + dy * dy + dz * dz, 1e-300), inv_r = rsqrt(r2), r = r2 * inv_r;
+      double g = 0.0;  // -dE/dR / R per unit n_T
+      if (A.chb_on && s_c[q] == chT) {
+        e_chb += nU * r2 * (A.kc * r2 - r + 1.0);
+        g -= A.de * nU * (4.0 * A.kc * r2 - 3.0 * r + 2.0);
       }
-      e_ev += nU * u * sR;
-      g -= nU * (du * sR + u * dsR) / r;
+      if (A.ev_on && r > A.r_lo) {
+        const double w = 1.0 / (r + A.rs), sw = A.sigma * w;
+        double wp;
+        if (A.ipower == 6) { const double s2 = sw * sw; wp = s2 * s2 * s2; }
+        else if (A.ipower == 3) wp = sw * sw * sw;
+        else wp = pow(sw, A.power);
+        const double u = A.eps * wp, du = -A.power * u * w;
+        double sR = 1.0, dsR = 0.0;
+        if (r < A.r_hi) {
+          const double t = (r - A.r_lo) * inv_band;
+          sR = t * t * (3.0 - 2.0 * t);
+          dsR = 6.0 * t * (1.0 - t) * inv_band;
+        }
+        e_ev += nU * u * sR;
+        g -= nU * (du * sR + u * dsR) * inv_r;
+      }
+      fx += g * dx; fy += g * dy; fz += g * dz;
     }
-    fx += g * dx; fy += g * dy; fz += g * dz;
   }
+  if (!live) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     fx += __shfl_xor_sync(0xffffffffu, fx, o);
