@@ -426,7 +426,7 @@ static bool any_pair_term(const mmm_system* h) {
 static int wanted_pair_mode(const mmm_system* h) {
   if (!any_pair_term(h)) return 0;
   if (h->cutoff > 0.0) return 3;
-  if (h->pair_kernel_pref != 1 && mmm_pair_n3_eligible(h)) return 2;
+  if (h->pair_kernel_pref != 1 && (mmm_pair_n3_eligible(h) || mmm_pair_n3_generic(h))) return 2;
   return 1;
 }
 
@@ -549,7 +549,7 @@ static int ensure_scratch(mmm_system* h) {
   if (h->nccl_comm) {
     const bool chb_ok = h->pp.chb_form < 0 || h->pp.chb_form == MMM_CHB_POLYNOMIAL;
     if (!(mode == 2 || (cut_n3 && chb_ok)))
-      return mmm_fail(h, MMM_ERR_STATE, "the multi-GPU path needs the Newton-3 kernel: default functional forms, EV on");
+      return mmm_fail(h, MMM_ERR_STATE, "the multi-GPU path needs the Newton-3 kernel (in cut-off mode: default functional forms, EV on)");
     h->d_epair = reinterpret_cast<double*>(h->d_facc + 3 * (size_t)h->npad);
     h->epair_aliased = true;
   } else {

@@ -269,6 +269,7 @@ bool mmm_pair_fast_path(const mmm_system* h);
 bool mmm_pair_fast_path_pp(const PairParams& p);
 // mmm_pair_n3.cu
 bool mmm_pair_n3_eligible(const mmm_system* h);
+bool mmm_pair_n3_generic(const mmm_system* h);
 int mmm_n3_build_items(mmm_system* h, std::vector<int2>& items, bool chb_only);
 int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only = false);  // d_pos4 -> d_facc, d_epair
 // mmm_dist.cu

@@ -47,6 +47,7 @@
 #include <algorithm>
 
 #include "mmm_internal.cuh"
+#include "mmm_pairmath.cuh"
 
 namespace {
 
@@ -133,6 +134,7 @@ struct N3Args {
   const int* perm;              // sorted slot -> bead id (force emission)
   double* npairs;               // [n_items] pairs inside the cut-off, per item
   N3Consts c;
+  PairParams pp;                // generic variant (EVP < 0) only: every functional form, FP64 body
 };
 
 
@@ -194,6 +196,7 @@ struct EAcc {
   float cnt;      // CUT: pairs inside the cut-off (reported through the CHB slot, which a CUT pass never uses)
   u64 cnt2;
   u64 scb2, cob2;  // packed partial sums of the Gaussian-range packed path
+  double gen[4];   // generic variant: EV, COB, SCB, CHB in kJ/mol (all prefactors applied)
 };
 
 // j-beads of a stage, laid out for the packed path: xy[j] = {-x, -x, -y, -y}, z[j] = {-z, -z}
@@ -439,6 +442,42 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
   }
 }
 
+// Generic variant (EVP < 0): any functional form of any pair term (model.py:205-211, 258-288, 338-378,
+// 424-445) and non-integer EV powers, through pairmath::pair_generic — FP32 deltas, FP64 after that — on
+// the Newton-3 machinery: every unordered pair once instead of the gather kernel's twice.  The slow path:
+// rolled loops, the i-beads indexed at run time (local memory), forces in kJ/mol/nm (U = 1).
+// "Particle 1" of the reference's s1-only Yukawa COB (model.py:262-266) is the lower index [OpenMM]: the
+// i side everywhere except in the diagonal stages, where ordered pairs are compared by index.
+template <bool SELF>
+__device__ __forceinline__ void pairs16_generic(const float4* __restrict__ sj, const int a, const int b, const int jj0,
+                                                IBeads& I, float (&cx)[2], float (&cy)[2], float (&cz)[2], EAcc& E,
+                                                const PairParams& pp, const int* __restrict__ si4, const int self_d) {
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    const int jl = (((jj0 + k) ^ a) << 2) | b;
+    const float4 pj = sj[jl];
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 1
+    for (int ii = 0; ii < 8; ++ii) {
+      pairmath::IBead ib;
+      ib.x = I.x(ii); ib.y = I.y(ii); ib.z = I.z(ii);
+      ib.w = si4[ii];
+      ib.a_scb = ib.a_cob = 0.0f;
+      bool live = true, i_lower = true;
+      if (SELF) {
+        live = (jl - ii) != self_d;
+        i_lower = (jl - ii) > self_d;  // j - i > 0
+      }
+      double px = 0.0, py = 0.0, pz = 0.0;
+      pairmath::pair_generic(pj, ib, (ib.w & 7) - 2, i_lower, pp, live, px, py, pz, E.gen);
+      const float fx = (float)px, fy = (float)py, fz = (float)pz;
+      I.fx[ii] += fx; I.fy[ii] += fy; I.fz[ii] += fz;
+      ax += fx; ay += fy; az += fz;
+    }
+    cx[k] = ax; cy[k] = ay; cz[k] = az;
+  }
+}
+
 #define N3_SHFL3(dst, src, m)                                  \
   dst##x = __shfl_xor_sync(0xffffffffu, src##x, m);            \
   dst##y = __shfl_xor_sync(0xffffffffu, src##y, m);            \
@@ -455,7 +494,7 @@ __device__ __forceinline__ void pairs16(const float4* __restrict__ sj, const int
 template <int EVP, int GK, int CHBM, bool SELF, bool WANT_J, bool CUT>
 __device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup sjd, const int a,
                                        const int b, IBeads& I, float (&out)[3], EAcc& E, const N3Consts& c,
-                                       const int* __restrict__ si4, const int self_d) {
+                                       const int* __restrict__ si4, const int self_d, const PairParams* pp = nullptr) {
   constexpr bool kPacked = N3_USE_F32X2 && GK == 0 && !SELF && (EVP > 0 ? CHBM <= 1 : CHBM == 1);
   constexpr bool kPackedNear = N3_USE_F32X2 && N3_PACKED_NEAR && GK != 0 && !SELF && EVP > 0 && CHBM <= 1;
   float s0x = 0.f, s0y = 0.f, s0z = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;  // saved group (g even)
@@ -463,7 +502,8 @@ __device__ __forceinline__ void step64(const float4* __restrict__ sj, const JDup
 #pragma unroll kGroupUnroll
   for (int g = 0; g < 4; ++g) {
     float cx[2], cy[2], cz[2];
-    if constexpr (kPacked) pairs16_packed<EVP, CHBM, CUT>(sjd, a, b, 2 * g, I, cx, cy, cz, E, c);
+    if constexpr (EVP < 0) pairs16_generic<SELF>(sj, a, b, 2 * g, I, cx, cy, cz, E, *pp, si4, self_d);
+    else if constexpr (kPacked) pairs16_packed<EVP, CHBM, CUT>(sjd, a, b, 2 * g, I, cx, cy, cz, E, c);
     else if constexpr (kPackedNear) pairs16_packed_near<EVP, GK, CHBM, CUT>(sj, sjd, a, b, 2 * g, I, cx, cy, cz, E, c, si4);
     else pairs16<EVP, GK, CHBM, SELF, CUT>(sj, a, b, 2 * g, I, cx, cy, cz, E, c, si4, self_d);
     if (!WANT_J) continue;
@@ -643,6 +683,7 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
         EAcc E;
         E.ev = E.scb = E.cob = E.chb = E.cnt = 0.0f;
         E.ev2 = E.chb2 = E.cnt2 = E.scb2 = E.cob2 = pk2(0.0f, 0.0f);
+        E.gen[0] = E.gen[1] = E.gen[2] = E.gen[3] = 0.0;
 
         if (!i_all_pad) {
           // Classify the stage's 8 tiles at once: lane s < 8 classifies tile s against this warp's
@@ -676,20 +717,20 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
             float fj[3];
             if (diag) {
               const int self_d = self_base - step * MMM_TILE;
-              step64<EVP, GK, CHB ? 2 : 0, true, false, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, self_d);
+              step64<EVP, GK, CHB ? 2 : 0, true, false, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, self_d, &A.pp);
               continue;  // ordered pairs: the j side is somebody's i side in this same stage pair
             }
             const int chb_mode = cls & 3;
             if (cls & 4) {
-              if (!CHB || chb_mode == 0) step64<EVP, GK, 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-              else if (chb_mode == 1) step64<EVP, GK, CHB ? 1 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
-              else step64<EVP, GK, CHB ? 2 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+              if (!CHB || chb_mode == 0) step64<EVP, GK, 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0, &A.pp);
+              else if (chb_mode == 1) step64<EVP, GK, CHB ? 1 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0, &A.pp);
+              else step64<EVP, GK, CHB ? 2 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0, &A.pp);
             } else if (!CHB || chb_mode == 0) {
-              step64<EVP, 0, 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+              step64<EVP, 0, 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0, &A.pp);
             } else if (chb_mode == 1) {
-              step64<EVP, 0, CHB ? 1 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+              step64<EVP, 0, CHB ? 1 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0, &A.pp);
             } else {
-              step64<EVP, 0, CHB ? 2 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0);
+              step64<EVP, 0, CHB ? 2 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0, &A.pp);
             }
             // lane (a, b) now holds j-bead 4 a + b = lane of this step; force on j is -sum
             const int col = step * MMM_TILE + lane;
@@ -707,10 +748,14 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
           if (CUT) { unpk2(E.cnt2, lo, hi); E.chb = E.cnt + lo + hi; }
         }
         const double wgt = diag ? 0.5 : 1.0;
-        de0 += wgt * (double)E.ev;
-        de1 += wgt * (double)E.cob;
-        de2 += wgt * (double)E.scb;
-        de3 += wgt * (double)E.chb;
+        if constexpr (EVP < 0) {
+          de0 += wgt * E.gen[0]; de1 += wgt * E.gen[1]; de2 += wgt * E.gen[2]; de3 += wgt * E.gen[3];
+        } else {
+          de0 += wgt * (double)E.ev;
+          de1 += wgt * (double)E.cob;
+          de2 += wgt * (double)E.scb;
+          de3 += wgt * (double)E.chb;
+        }
 
         if (more) {
           s_j[buf ^ 1][tid] = nxt;
@@ -1049,6 +1094,7 @@ void fill_consts(const PairParams& p, bool chb_only, bool with_chb, N3Args& A) {
   // U = p eps sigma^p in double, from the float parameters the gather kernel uses too (1 in the
   // CHB-only pass, where EV is not evaluated)
   const double U = chb_only ? 1.0 : (double)p.ev_power * (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
+  A.pp = p;
   A.fscale = U * N3_FIXED;
   A.e_ev = chb_only ? 0.0 : (double)p.ev_eps * pow((double)p.ev_sigma, (double)p.ev_power);
   N3Consts& c = A.c;
@@ -1084,6 +1130,14 @@ bool mmm_pair_n3_eligible(const mmm_system* h) {
   if (h->pp.ev_form != MMM_EV_POWERLAW) return false;
   if (!(h->pp.ev_eps > 0.0f) || !(h->pp.ev_sigma > 0.0f)) return false;
   return true;
+}
+
+// Every other combination of functional forms (and non-integer EV powers) takes the same machinery with
+// the generic FP64 body (k_pair_n3<-1, 0, false, false>): exact mode only.
+bool mmm_pair_n3_generic(const mmm_system* h) {
+  const PairParams& p = h->pp;
+  const bool any = p.ev_form >= 0 || p.cob_form >= 0 || p.scb_form >= 0 || p.chb_form >= 0;
+  return any && !mmm_pair_fast_path(h);
 }
 
 // Work items: for every i-block, runs of at most cj j-stages starting at the diagonal.
@@ -1149,6 +1203,11 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
   A.npairs = nullptr;
   A.sys_counter = 0;
   fill_consts(p, chb_only, true, A);
+  const bool generic = !chb_only && !mmm_pair_n3_eligible(h);
+  if (generic) {  // forces and energies leave the generic body with every prefactor applied
+    A.fscale = N3_FIXED;
+    A.e_ev = A.e_gauss = A.e_chb = 1.0;
+  }
   const N3Consts& c = A.c;
 
   const bool timed = !chb_only;  // the CHB-only pass is timed with the cell-list pass
@@ -1178,6 +1237,7 @@ int mmm_launch_pair_n3(mmm_system* h, const int* d_skip, bool chb_only) {
       MMM_CUDA(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream));
     }
     if (chb_only) launch_n3<0, 0, true, false>(h, A);
+    else if (generic) launch_n3<-1, 0, false, false>(h, A);
     else if (p.ev_power == 6.0f) launch_n3_evp<6>(h, A, c.gk, chb);
     else launch_n3_evp<3>(h, A, c.gk, chb);
     h->launches++;

@@ -76,6 +76,9 @@ def test_pair_kernel_resources_allow_two_ctas_per_sm(built_lib):
     for name, reg, stack, shared in rows:
         assert int(reg) <= 128, (name, reg)
         assert int(shared) <= 48 * 1024, (name, shared)
+        if "k_pair_n3ILin1E" in name:  # the generic variant (EVP = -1): FP64 body, i-beads indexed at run time
+            assert int(stack) <= 512, (name, stack)  # (local memory by design: the slow path)
+            continue
         assert int(stack) <= 192, (name, stack)  # spilled words live in the rare variants' prologues, never in a pair loop
     gw = [n for n, *_ in rows if "k_pair_n3ILi6ELi1ELb1" in n]
     assert len(gw) == 1
