@@ -732,11 +732,12 @@ __global__ void __launch_bounds__(N3_THREADS, N3_MIN_BLOCKS) k_pair_n3(const N3A
             } else {
               step64<EVP, 0, CHB ? 2 : 0, false, true, CUT>(sj, sjd, a, b, I, fj, E, c, s_it + iw, 0, &A.pp);
             }
-            // lane (a, b) now holds j-bead 4 a + b = lane of this step; force on j is -sum
+            // lane (a, b) now holds j-bead 4 a + b = lane of this step; force on j is -sum.  A warp writes a
+            // column at most once per stage and the emission below leaves it zero: a plain store, no read
             const int col = step * MMM_TILE + lane;
-            s_acc[warp][0][col] -= fj[0];
-            s_acc[warp][1][col] -= fj[1];
-            s_acc[warp][2][col] -= fj[2];
+            s_acc[warp][0][col] = -fj[0];
+            s_acc[warp][1][col] = -fj[1];
+            s_acc[warp][2][col] = -fj[2];
           }
         }
         {
