@@ -24,9 +24,40 @@ import tarfile
 import time
 from enum import Enum
 
-from . import loaders
-from .config import SimulationConfig
-from .units import Quantity
+
+def _early_cuda_start():
+    """Ensemble worker processes only (run_ensemble exports MMM_WORKER_WARMUP=1 to them): CUDA
+    initialisation — several seconds per process when eight start at once on an 8-GPU box — begins on a
+    background thread BEFORE this module's own imports (pandas, pydantic: ~3 s) and the first member's
+    input ingestion, instead of after them.  ctypes releases the GIL, so the two overlap.  The thread only
+    creates and destroys a two-bead handle; whatever is wrong with the device is reported by the member's
+    own mmm_create later."""
+    if os.environ.get("MMM_WORKER_WARMUP") != "1":
+        return None
+    import threading
+
+    def warm():
+        try:
+            import ctypes
+
+            from . import _lib
+            lib = _lib.load()
+            h = ctypes.c_void_p()
+            if lib.mmm_create(0, 2, ctypes.byref(h)) == 0:
+                lib.mmm_destroy(h)
+        except Exception:  # noqa: BLE001
+            pass
+
+    t = threading.Thread(target=warm, name="mmm-cuda-warmup", daemon=True)
+    t.start()
+    return t
+
+
+_WARMUP = _early_cuda_start()
+
+from . import loaders  # noqa: E402
+from .config import SimulationConfig  # noqa: E402
+from .units import Quantity  # noqa: E402
 
 logger = logging.getLogger("multimm_b200")
 
@@ -378,20 +409,36 @@ def _take(todo_queue):
             return
 
 
-def _worker(params: dict, paths: list[str], todo_queue, device: int, archive: bool, queue):
-    # One GPU per worker process: with only its own device visible, CUDA initialisation does not touch
-    # the other seven (eight processes initialising an 8-GPU box at once took ~10 s each otherwise).
-    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+def worker_environment(device: int, base: dict | None = None) -> tuple[dict, int]:
+    """Environment of the worker process that drives GPU `device`, and the device index it will use.
+    One GPU per worker: with only its own device visible, CUDA initialisation does not touch the other
+    seven.  The restriction is exported by the PARENT before the worker starts (run_ensemble), because the
+    worker begins to initialise CUDA while it is still importing (_early_cuda_start)."""
+    env = dict(os.environ if base is None else base)
+    visible = env.get("CUDA_VISIBLE_DEVICES")
+    local = 0
     if visible is None:
-        os.environ["CUDA_VISIBLE_DEVICES"] = str(device)
-        local = 0
+        env["CUDA_VISIBLE_DEVICES"] = str(device)
     else:  # the parent already runs under a restriction: `device` indexes into it
         ids = [t for t in visible.split(",") if t.strip()]
         if device < len(ids):
-            os.environ["CUDA_VISIBLE_DEVICES"] = ids[device]
-            local = 0
+            env["CUDA_VISIBLE_DEVICES"] = ids[device]
         else:
             local = device  # nothing sensible to narrow to: let mmm_create report it
+    # MMM_NO_EARLY_CUDA=1 switches the early start off (A/B timing)
+    env["MMM_WORKER_WARMUP"] = "1" if local == 0 and os.environ.get("MMM_NO_EARLY_CUDA") != "1" else "0"
+    env["MMM_WORKER_LOCAL_DEVICE"] = str(local)
+    return env, local
+
+
+def _worker(params: dict, paths: list[str], todo_queue, device: int, archive: bool, queue):
+    # the parent exported this worker's CUDA_VISIBLE_DEVICES (worker_environment); a worker started by
+    # other means narrows the visible devices itself, before anything has touched CUDA
+    if "MMM_WORKER_LOCAL_DEVICE" in os.environ:
+        local = int(os.environ["MMM_WORKER_LOCAL_DEVICE"])
+    else:
+        env, local = worker_environment(device)
+        os.environ["CUDA_VISIBLE_DEVICES"] = env["CUDA_VISIBLE_DEVICES"]
 
     def emit(msg):
         kind, payload = msg
@@ -427,8 +474,22 @@ def run_ensemble(args, devices: list[int] | None = None, archive: bool = True) -
         todo_queue.put(i)
     procs = [ctx.Process(target=_worker, args=(params, paths, todo_queue, dev, archive, queue))
              for dev in devices[:n]]
-    for p in procs:
-        p.start()
+    # a spawned child inherits os.environ as it is at start(): export each worker's own restriction
+    # (and the early CUDA start) around its start, then put the parent's environment back
+    keys = ("CUDA_VISIBLE_DEVICES", "MMM_WORKER_WARMUP", "MMM_WORKER_LOCAL_DEVICE")
+    saved = {k: os.environ.get(k) for k in keys}
+    try:
+        for p, dev in zip(procs, devices[:n]):
+            env, _ = worker_environment(dev, base={k: v for k, v in saved.items() if v is not None})
+            for k in keys:
+                os.environ[k] = env[k]
+            p.start()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     try:
         results, errors = collect_reports(procs, queue, n)
     finally:

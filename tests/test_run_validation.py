@@ -316,3 +316,41 @@ def test_archiver_runs_in_the_background_and_reports_failures(tmp_path):
     arch.submit(str(tmp_path / "does_not_exist"))
     with pytest.raises(Exception):
         arch.wait()
+
+
+def test_worker_environment_and_early_cuda_start(monkeypatch):
+    """One visible device per ensemble worker, exported by the parent before the worker starts (the worker
+    begins to initialise CUDA while it is still importing); the parent's own environment is untouched."""
+    import threading
+
+    from multimm_b200 import run
+
+    env, local = run.worker_environment(3, base={})
+    assert (env["CUDA_VISIBLE_DEVICES"], local, env["MMM_WORKER_WARMUP"], env["MMM_WORKER_LOCAL_DEVICE"]) == ("3", 0, "1", "0")
+    env, local = run.worker_environment(1, base={"CUDA_VISIBLE_DEVICES": "4,6"})
+    assert (env["CUDA_VISIBLE_DEVICES"], local) == ("6", 0)
+    env, local = run.worker_environment(5, base={"CUDA_VISIBLE_DEVICES": "4,6"})  # nothing to narrow to
+    assert (env["CUDA_VISIBLE_DEVICES"], local, env["MMM_WORKER_WARMUP"]) == ("4,6", 5, "0")
+    # outside a worker nothing is started at import
+    monkeypatch.delenv("MMM_WORKER_WARMUP", raising=False)
+    assert run._early_cuda_start() is None
+    # inside one a daemon thread is (here it fails quietly: no device, or no library)
+    monkeypatch.setenv("MMM_WORKER_WARMUP", "1")
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "")
+    t = run._early_cuda_start()
+    assert isinstance(t, threading.Thread) and t.daemon
+    t.join(timeout=60)
+    assert not t.is_alive()
+
+
+def test_run_ensemble_leaves_the_parents_environment_alone(tmp_path, monkeypatch):
+    from multimm_b200 import run
+
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "")
+    monkeypatch.delenv("MMM_WORKER_WARMUP", raising=False)
+    monkeypatch.delenv("MMM_WORKER_LOCAL_DEVICE", raising=False)
+    args = make_config(GENERATE_ENSEMBLE=True, N_ENSEMBLE=2, OUT_PATH=str(tmp_path / "out"))
+    with pytest.raises(RuntimeError, match="ensemble member"):
+        run.run_ensemble(args, devices=[0, 1])  # no device: both workers report a failure
+    assert os.environ.get("CUDA_VISIBLE_DEVICES") == ""
+    assert "MMM_WORKER_WARMUP" not in os.environ and "MMM_WORKER_LOCAL_DEVICE" not in os.environ
