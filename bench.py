@@ -344,6 +344,12 @@ def structures_per_hour(world: int, slowest_seconds: float) -> float:
     return world * 3600.0 / slowest_seconds
 
 
+def run_pipeline_on() -> bool:
+    from multimm_b200 import run
+
+    return run.pipeline_enabled()
+
+
 def ensemble_members(workload: str, rank: int, world: int, device: int, tmp: str, coarse_cutoff: float, count: int) -> dict:
     """`count` ensemble members on this rank's GPU through the driver's per-replica pipeline
     (multimm_b200.run.run_replicas_on_device == the loop at run.py:473-485): parse inputs, Hilbert
@@ -461,22 +467,32 @@ def run_ours(opt):
         ens = None
         if not opt.no_ensemble and opt.workload != "stress" and not decomposed:
             barrier()
-            mine = ensemble_members(opt.workload, rank, world, local, tmp, opt.coarse_cutoff, opt.ensemble_members)
+            ens_error = None
+            try:
+                mine = ensemble_members(opt.workload, rank, world, local, tmp, opt.coarse_cutoff, opt.ensemble_members)
+            except Exception as e:  # this object is an add-on to the contract line: a failure must not cost the line
+                mine, ens_error = dict(wall_seconds=1e30, members=[]), f"{type(e).__name__}: {e}"
             slow = max_over_ranks([mine["wall_seconds"]], device=dev)[0]
             keep = ("replica", "seconds", "iterations", "evaluations", "e_final", "converged", "initialize_s",
                     "forcefield_s", "minimize_s", "write_cif_s", "coarse_iterations", "coarse_seconds", "coarse_rounds",
-                    "exact_iterations", "archive_inline_s")
+                    "exact_iterations", "archive_inline_s", "prepare_s", "compute_s", "finish_s")
             members = world * opt.ensemble_members
-            ens = dict(structures_per_hour=members * 3600.0 / slow, members=members, members_per_gpu=opt.ensemble_members,
-                       gpus=world, slowest_rank_seconds=slow, unit="structures/hour",
-                       mode=(f"opt-in two-stage minimisation (MIN_COARSE_CUTOFF = {opt.coarse_cutoff} nm, then the exact "
-                             "potential to the same stopping rule)" if opt.coarse_cutoff > 0 else
-                             "reference semantics (exact potential throughout)"),
-                       pipeline="run.run_replicas_on_device: loaders, Hilbert start, init CIF + PSF, force field, minimisation, "
-                                "minimised CIF, per-chromosome CIFs, tar.gz (run.py:473-485); the archive of member k is "
-                                "written on a background thread while member k + 1 minimises",
-                       rank0_members=[{k: r[k] for k in keep if k in r} for r in mine["members"]])
-            if mini_full is not None and opt.coarse_cutoff > 0:
+            if slow >= 1e29:
+                ens = dict(error=ens_error or "an ensemble member failed on another rank", members=members, gpus=world)
+            else:
+                ens = dict(structures_per_hour=members * 3600.0 / slow, members=members, members_per_gpu=opt.ensemble_members,
+                           gpus=world, slowest_rank_seconds=slow, unit="structures/hour",
+                           mode=(f"opt-in two-stage minimisation (MIN_COARSE_CUTOFF = {opt.coarse_cutoff} nm, then the exact "
+                                 "potential to the same stopping rule)" if opt.coarse_cutoff > 0 else
+                                 "reference semantics (exact potential throughout)"),
+                           pipeline="run.run_replicas_on_device: loaders, Hilbert start, init CIF + PSF, force field, minimisation, "
+                                    "minimised CIF, per-chromosome CIFs, tar.gz (run.py:473-485); member k + 1 is prepared and "
+                                    "member k - 1 written out and archived on background threads while member k minimises"
+                                    if run_pipeline_on() else
+                                    "run.run_replicas_on_device, MMM_ENSEMBLE_PIPELINE=0: members one after another, only the "
+                                    "tar.gz in the background",
+                           rank0_members=[{k: r[k] for k in keep if k in r} for r in mine["members"]])
+            if mini_full is not None and opt.coarse_cutoff > 0 and ens.get("rank0_members"):
                 mini_full["two_stage"] = dict(ens["rank0_members"][0], coarse_cutoff_nm=opt.coarse_cutoff,
                                               note="minimize_s = both stages; same stopping rule met on the exact potential")
 

@@ -309,9 +309,10 @@ class MultiMM:
         self.timings["exact_iterations"], self.timings["exact_evaluations"] = e_it, e_ev
         return rep
 
-    def min_energy(self):
+    def min_energy(self, write_files: bool = True):
         """model.py:859-897: minimise with OpenMM's defaults (10 kJ/mol/nm, unlimited iterations)
-        and write model/MultiMM_minimized.cif (Angstrom)."""
+        and write model/MultiMM_minimized.cif (Angstrom).  write_files False: the file is left to
+        write_minimized() (the ensemble driver writes it while the next member minimises)."""
         a = self.args
         t0 = time.time()
         tol, max_iter = float(getattr(a, "MIN_TOLERANCE", 10.0)), int(getattr(a, "MIN_MAX_ITERATIONS", 0))
@@ -327,14 +328,20 @@ class MultiMM:
         else:
             self.report = self.engine.minimize(tol=tol, max_iter=max_iter)
         self.positions = self.engine.get_positions()
+        self.positions_minimized = self.positions
         self.timings["minimize_s"] = time.time() - t0
-        t1 = time.time()
-        cif.write_mmcif(10.0 * self.positions, self.chr_ends, self.save_path + "model/MultiMM_minimized.cif",
-                        hetatm_ends=True, connections=False, decimals=4)
-        self.timings["write_cif_s"] = time.time() - t1
+        if write_files:
+            self.write_minimized()
         dt = time.time() - t0
         logger.info(f"--- Energy minimization done!! Executed in {dt // 3600:.0f} hours, {dt % 3600 // 60:.0f} "
                     f"minutes and  {dt % 60:.0f} seconds. :D --- {self.report}")
+
+    def write_minimized(self):
+        """model/MultiMM_minimized.cif (model.py:889-896), Angstrom."""
+        t1 = time.time()
+        cif.write_mmcif(10.0 * self.positions_minimized, self.chr_ends, self.save_path + "model/MultiMM_minimized.cif",
+                        hetatm_ends=True, connections=False, decimals=4)
+        self.timings["write_cif_s"] = time.time() - t1
 
     def run_md(self):
         """model.py:907-995: relaxation with the configured integrator, a thermodynamic record every
@@ -393,7 +400,7 @@ class MultiMM:
         """model.py:899-905."""
         for k in range(len(self.chr_ends) - 1):
             name = loaders.CHROM_NAMES[int(self.chrom_idxs[k])]
-            cif.write_mmcif_chrom(10.0 * self.positions[self.chr_ends[k]:self.chr_ends[k + 1]],
+            cif.write_mmcif_chrom(10.0 * self.positions_minimized[self.chr_ends[k]:self.chr_ends[k + 1]],
                                   self.save_path + f"model/chromosomes/MultiMM_minimized_{name}.cif")
 
     def make_reports(self):
@@ -423,20 +430,38 @@ class MultiMM:
                 else:
                     f.write(f"{name} = {getattr(value, 'value', value)}\n")
 
-    def run(self):
-        """model.py:1216-1248."""
+    # run() = prepare() -> compute() -> finish() (model.py:1216-1248).  The split is what the ensemble
+    # driver pipelines: member k + 1 is prepared and member k - 1 written out while member k computes.
+    def prepare(self):
+        """Everything up to the first force evaluation: radii, start structure and its files, the engine,
+        the force field.  The only stage (besides __init__) that draws from numpy's global random stream
+        (the random start curves), so it must follow the member's own __init__ with nothing in between."""
         self.set_radiuses()
         self.initialize_simulation()
         self.add_forcefield()
-        self.min_energy()
-        if self._whole:
-            self.save_chromosomes()
+
+    def compute(self):
+        """The GPU-bound stage: minimisation, MD relaxation if configured.  No structure files except MD's."""
+        self.min_energy(write_files=False)
         if self.args.SIM_RUN_MD:
             self.run_md()
+
+    def finish(self):
+        """Structure files, per-chromosome files, reports, parameters.  Host work (the report's device
+        pass takes the device index, not this member's engine)."""
+        self.write_minimized()
+        if self._whole:
+            self.save_chromosomes()  # the minimised structure, as model.py:1222-1224 (before MD)
         if self.args.SAVE_PLOTS:
             self.make_reports()
         self.save_args_to_txt(self.args.OUT_PATH + "/metadata/parameters.txt")
         return self.report
+
+    def run(self):
+        """model.py:1216-1248."""
+        self.prepare()
+        self.compute()
+        return self.finish()
 
     def close(self):
         if self.engine is not None:

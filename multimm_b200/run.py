@@ -326,8 +326,7 @@ class Archiver:
 def build_replica(params: dict, i: int, run_path: str, device: int):
     """Host side of one ensemble member up to the point where the GPU is needed: config with
     SHUFFLING_SEED = i and OUT_PATH = run_<i> (run.py:473-476), output tree, input ingestion
-    (MultiMM.__init__: the loaders).  Pure host work: the driver runs it for member k + 1 on a background
-    thread while member k minimises."""
+    (MultiMM.__init__: the loaders)."""
     from .model import MultiMM
 
     cfg = SimulationConfig(**{**params, "SHUFFLING_SEED": i, "OUT_PATH": run_path})
@@ -338,17 +337,35 @@ def build_replica(params: dict, i: int, run_path: str, device: int):
     return md
 
 
-def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool = True, archiver: Archiver | None = None,
-                prebuilt=None) -> dict:
-    """One ensemble member (run.py:473-485).  With an `archiver` the tar.gz is written in the background
-    (the report names the file it will be); `prebuilt`: the member's MultiMM object from build_replica."""
+def prepare_replica(params: dict, i: int, run_path: str, device: int):
+    """build_replica + MultiMM.prepare(): everything of member i that precedes its first force
+    evaluation, in ONE task — __init__ seeds numpy's global random stream with the member's
+    SHUFFLING_SEED and the random start curves of prepare() go on drawing from it, so nothing else that
+    draws may come between the two (the pipelined driver runs these tasks one after another on one thread,
+    and no other stage draws)."""
     t0 = time.time()
-    md = prebuilt if prebuilt is not None else build_replica(params, i, run_path, device)
+    md = build_replica(params, i, run_path, device)
     try:
-        rep = md.run()
+        md.prepare()
+    except BaseException:
+        md.close()
+        raise
+    md.timings["prepare_s"] = time.time() - t0
+    return md
+
+
+def finish_replica(md, i: int, run_path: str, device: int, compute_s: float, archive: bool,
+                   archiver: Archiver | None) -> dict:
+    """Write-out of a computed member: structure files, reports, engine released, archive queued."""
+    t0 = time.time()
+    try:
+        rep = md.finish()
     finally:
         md.close()
-    out = dict(replica=i, device=device, seconds=time.time() - t0, **(rep or {}), **md.timings)
+    finish_s = time.time() - t0
+    prepare_s = md.timings.get("prepare_s", 0.0)
+    out = dict(replica=i, device=device, seconds=prepare_s + compute_s + finish_s, compute_s=compute_s,
+               finish_s=finish_s, **(rep or {}), **md.timings)
     if archive:
         t1 = time.time()
         if archiver is not None:
@@ -360,20 +377,62 @@ def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool 
     return out
 
 
+def run_replica(params: dict, i: int, run_path: str, device: int, archive: bool = True, archiver: Archiver | None = None,
+                prebuilt=None) -> dict:
+    """One ensemble member from start to end on the calling thread (run.py:473-485).  With an `archiver`
+    the tar.gz is written in the background (the report names the file it will be)."""
+    md = prebuilt if prebuilt is not None else prepare_replica(params, i, run_path, device)
+    t0 = time.time()
+    try:
+        md.compute()
+    except BaseException:
+        md.close()
+        raise
+    return finish_replica(md, i, run_path, device, time.time() - t0, archive, archiver)
+
+
+def pipeline_enabled() -> bool:
+    """MMM_ENSEMBLE_PIPELINE=0: every member runs from start to end on one thread (only the tar.gz of the
+    previous member is written in the background)."""
+    return os.environ.get("MMM_ENSEMBLE_PIPELINE", "1") != "0"
+
+
 def run_replicas_on_device(params: dict, paths: list[str], todo, device: int, archive: bool, emit):
-    """The replicas one GPU takes, one after another.  Two things overlap the minimisation of member k:
-    the tar.gz of member k - 1 (Archiver) and the input ingestion of member k + 1 (build_replica on a
-    background thread; gzip, pandas' parsers and the engine's C calls release the GIL)."""
+    """The replicas one GPU takes.  Three stages run side by side so that the GPU goes from one
+    minimisation straight into the next: member k + 1 is PREPARED (inputs read, start structure and its
+    files, engine, force field) on one background thread, member k COMPUTES (minimisation, MD) on the
+    calling thread, member k - 1 is WRITTEN OUT (structure files, reports; then its tar.gz by the Archiver)
+    on another.  pandas' parsers, file writes, gzip and every engine call release the GIL; the engine's
+    graph capture is thread-local.  At most one member waits in each stage (bounded memory)."""
     from concurrent.futures import ThreadPoolExecutor
 
     archiver = Archiver() if archive else None
-    prefetch = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mmm-ingest")
+    if not pipeline_enabled():
+        try:
+            for i in todo:
+                try:
+                    emit(("ok", run_replica(params, i, paths[i], device, archive, archiver)))
+                except Exception as e:  # report and keep going with the next replica
+                    emit(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
+        finally:
+            _wait_archiver(archiver, emit, device)
+        return
+
+    prep = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mmm-prepare")
+    fin = ThreadPoolExecutor(max_workers=1, thread_name_prefix="mmm-finish")
     it = iter(todo)
 
     def start_next():
         i = next(it, None)
-        return None if i is None else (i, prefetch.submit(build_replica, params, i, paths[i], device))
+        return None if i is None else (i, prep.submit(prepare_replica, params, i, paths[i], device))
 
+    def finish_and_emit(md, i, compute_s):
+        try:
+            emit(("ok", finish_replica(md, i, paths[i], device, compute_s, archive, archiver)))
+        except Exception as e:
+            emit(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
+
+    finishing = None
     try:
         pending = start_next()
         while pending is not None:
@@ -384,18 +443,32 @@ def run_replicas_on_device(params: dict, paths: list[str], todo, device: int, ar
                 pending = start_next()
                 emit(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
                 continue
-            pending = start_next()  # member k + 1 is ingested while member k runs
+            pending = start_next()  # member k + 1 is prepared while member k computes
+            t0 = time.time()
             try:
-                emit(("ok", run_replica(params, i, paths[i], device, archive, archiver, prebuilt=md)))
+                md.compute()
             except Exception as e:  # report and keep going with the next replica
+                md.close()
                 emit(("error", dict(replica=i, device=device, error=f"{type(e).__name__}: {e}")))
+                continue
+            if finishing is not None:
+                finishing.result()  # never more than one member behind
+            finishing = fin.submit(finish_and_emit, md, i, time.time() - t0)
     finally:
-        prefetch.shutdown(wait=True)
-        if archiver is not None:
-            try:
-                archiver.wait()
-            except Exception as e:
-                emit(("error", dict(replica=-1, device=device, error=f"archive failed: {type(e).__name__}: {e}")))
+        if finishing is not None:
+            finishing.result()
+        prep.shutdown(wait=True)
+        fin.shutdown(wait=True)
+        _wait_archiver(archiver, emit, device)
+
+
+def _wait_archiver(archiver, emit, device):
+    if archiver is None:
+        return
+    try:
+        archiver.wait()
+    except Exception as e:
+        emit(("error", dict(replica=-1, device=device, error=f"archive failed: {type(e).__name__}: {e}")))
 
 
 def _take(todo_queue):
