@@ -188,3 +188,57 @@ def test_gene_level_without_the_table_fails_early(tmp_path, monkeypatch):
     with pytest.raises(ValueError, match="GENE_TSV"):
         model.MultiMM(args)
     assert not out.exists()
+
+
+def test_run_is_prepare_compute_finish_and_writes_the_minimised_structure_files(tmp_path, monkeypatch):
+    """run() = prepare() -> compute() -> finish() (model.py:1216-1248): the engine is driven in that order,
+    model/MultiMM_minimized.cif and the per-chromosome files hold the MINIMISED structure even when an MD
+    relaxation moved the beads afterwards (the reference saves the chromosomes before MD, model.py:1222-1226),
+    and parameters.txt is written last."""
+    from multimm_b200 import cif
+
+    class Moving(Recorder):
+        """positions: 1 nm after the minimisation, 2 nm after MD"""
+        def __getattr__(self, name):
+            base = super().__getattr__(name)
+            if name == "get_positions":
+                def pos(*a, **k):
+                    base(*a, **k)
+                    md_done = any(n == "md_run" for n, _, _ in self.calls)
+                    return np.full((self.n, 3), 2.0 if md_done else 1.0)
+                return pos
+            if name == "md_run":
+                def md_run(*a, **k):
+                    base(*a, **k)
+                    return dict(step=0, potential=0.0, kinetic=0.0, temperature=0.0)
+                return md_run
+            return base
+
+    monkeypatch.setattr(model, "Engine", Moving)
+    out = tmp_path / "o"
+    args = SimulationConfig(PLATFORM="B200", N_BEADS=3000, LOOPS_PATH=BEDPE, OUT_PATH=str(out), SAVE_PLOTS=False,
+                            SIM_RUN_MD=True, SIM_N_STEPS=20, SIM_SAMPLING_STEP=10, TRJ_FRAMES=2)
+    m = model.MultiMM(args)
+    rep = m.run()
+    assert rep["converged"] == 1
+    names = [n for n, _, _ in m.engine.calls]
+    assert names.index("hilbert_init") < names.index("set_pair_term") < names.index("minimize") < names.index("md_run")
+    mini = cif.read_cif_coordinates(str(out / "model/MultiMM_minimized.cif"), include_hetatm=True)
+    after = cif.read_cif_coordinates(str(out / "model/MultiMM_afterMD.cif"), include_hetatm=True)
+    assert np.allclose(mini, 10.0) and np.allclose(after, 20.0)  # Angstrom
+    chrom_files = sorted(os.listdir(out / "model" / "chromosomes"))
+    assert chrom_files, "per-chromosome files of the minimised structure"
+    one = cif.read_cif_coordinates(str(out / "model" / "chromosomes" / chrom_files[0]), include_hetatm=True)
+    assert np.allclose(one, 10.0)
+    assert (out / "metadata" / "parameters.txt").exists()
+    # the same three stages called one by one (what the ensemble driver does) leave the same files
+    out2 = tmp_path / "o2"
+    m2 = model.MultiMM(SimulationConfig(**{**args.model_dump(), "OUT_PATH": str(out2)}))
+    m2.prepare()
+    assert not (out2 / "model/MultiMM_minimized.cif").exists()
+    m2.compute()
+    assert not (out2 / "model/MultiMM_minimized.cif").exists()  # left to finish(): written while the next member minimises
+    m2.finish()
+    for rel in ("model/MultiMM_minimized.cif", "model/MultiMM_afterMD.cif", "model/chromosomes/" + chrom_files[0]):
+        assert (out / rel).read_bytes() == (out2 / rel).read_bytes(), rel
+    assert (out2 / "metadata" / "parameters.txt").exists()
